@@ -1,0 +1,171 @@
+"""Pin the CPU oracle against vectors produced by the unmodified reference
+(tests/golden/make_golden.py).  CPU-only."""
+import numpy as np
+import pytest
+
+from oracle import bigvgan_oracle as O
+from svc_inference_pipeline_b200.utils import synth
+
+TINY = {
+    "resblock_kernel_sizes": [3, 7],
+    "upsample_rates": [4, 2],
+    "input_dim": 10,
+    "upsample_initial_channel": 32,
+    "resblock": "1",
+    "upsample_kernel_sizes": [8, 4],
+    "resblock_dilation_sizes": [[1, 3, 5], [1, 3, 5]],
+    "activation": "snakebeta",
+    "snake_logscale": True,
+}
+TINY_VARIANTS = {
+    "b1_snakebeta_log": dict(),
+    "b2_snake_lin": dict(resblock="2", activation="snake", snake_logscale=False, resblock_dilation_sizes=[[1, 3], [1, 3]]),
+    "b1_snake_log": dict(activation="snake"),
+    "b2_snakebeta_lin": dict(resblock="2", snake_logscale=False, resblock_dilation_sizes=[[1, 3], [1, 3]]),
+}
+REPO = dict(TINY, resblock_kernel_sizes=[3, 7, 11], upsample_rates=[4, 4, 2, 2, 2, 2], input_dim=100,
+            upsample_initial_channel=1536, upsample_kernel_sizes=[8, 8, 4, 4, 4, 4],
+            resblock_dilation_sizes=[[1, 3, 5]] * 3)
+
+
+def tiny_sd(tag):
+    cfg = dict(TINY, **TINY_VARIANTS[tag])
+    sd = synth.synthetic_state_dict(cfg, seed=7)
+    if not cfg["snake_logscale"]:
+        for k in sd:
+            if k.endswith(".alpha") or k.endswith(".beta"):
+                sd[k] = (1.0 + 0.6 * sd[k]).astype(np.float32)
+    return cfg, sd
+
+
+@pytest.mark.parametrize("tag", ["aa12", "odd9", "k24", "lowatt", "noatt"])
+def test_filter_design(golden, tag):
+    g = golden("filters.npz")
+    cut, hw, k = g[tag + "_args"]
+    f = O.kaiser_sinc_filter1d(float(cut), float(hw), int(k))
+    np.testing.assert_allclose(f, g[tag], rtol=0, atol=2e-7)
+    assert abs(f.sum() - 1.0) < 1e-6
+
+
+def test_filter_known_taps(golden):
+    # SURVEY.md section 8 a1 golden constants
+    taps = [0.0020289647, 0.0093894657, -0.0255434588, -0.0576573834, 0.1285725832, 0.4432097971]
+    f = synth.aa_filter_taps()
+    np.testing.assert_allclose(f[:6], taps, atol=2e-7)
+    np.testing.assert_allclose(f[::-1], f, atol=0)
+    np.testing.assert_allclose(f, golden("filters.npz")["aa12"], atol=2e-7)
+
+
+def test_resamplers(golden):
+    g = golden("activation1d.npz")
+    f = golden("filters.npz")["aa12"]
+    x = g["x"]
+    up = O.upsample1d(x, f)
+    np.testing.assert_allclose(up, g["up"], atol=2e-6)
+    np.testing.assert_allclose(O.upsample2x_closed_form(x, f), g["up"], atol=2e-6)
+    np.testing.assert_allclose(O.upsample1d(x.astype(np.float64), f.astype(np.float64)), g["up_f64"], atol=1e-13)
+    np.testing.assert_allclose(O.upsample2x_closed_form(x.astype(np.float64), f.astype(np.float64)), g["up_f64"], atol=1e-13)
+    np.testing.assert_allclose(O.lowpass_downsample1d(g["up"], f), g["down_of_up"], atol=2e-6)
+    np.testing.assert_allclose(O.downsample2x_closed_form(g["up"], f), g["down_of_up"], atol=2e-6)
+
+
+@pytest.mark.parametrize("name", ["snake", "snakebeta"])
+@pytest.mark.parametrize("scale", ["lin", "log"])
+def test_activation1d(golden, name, scale):
+    g = golden("activation1d.npz")
+    f = golden("filters.npz")["aa12"]
+    log = scale == "log"
+    alpha = g["alpha"] if log else 1.0 + 0.3 * g["alpha"]
+    beta = None if name == "snake" else (g["beta"] if log else 1.0 + 0.3 * g["beta"])
+    tag = f"{name}_{scale}"
+    np.testing.assert_allclose(O.snake(g["x"], alpha.astype(np.float32), None if beta is None else beta.astype(np.float32), log), g[tag + "_act"], atol=3e-6, rtol=1e-6)
+    y = O.activation1d(g["x"], alpha.astype(np.float32), None if beta is None else beta.astype(np.float32), log, f, f)
+    np.testing.assert_allclose(y, g[tag + "_a1d"], atol=5e-6, rtol=1e-6)
+    y64 = O.activation1d(g["x"].astype(np.float64), alpha.astype(np.float32).astype(np.float64), None if beta is None else beta.astype(np.float32).astype(np.float64), log, f.astype(np.float64), f.astype(np.float64))
+    np.testing.assert_allclose(y64, g[tag + "_a1d_f64"], atol=1e-12)
+
+
+@pytest.mark.parametrize("ln", [1, 2, 3, 5, 6, 11, 12, 13])
+def test_activation1d_edges(golden, ln):
+    g = golden("activation1d.npz")
+    f = golden("filters.npz")["aa12"]
+    y = O.activation1d(g[f"edge{ln}_x"], g["alpha"][:3], g["beta"][:3], True, f, f)
+    np.testing.assert_allclose(y, g[f"edge{ln}_y"], atol=1e-5, rtol=1e-6)
+
+
+def test_activation1d_large_argument(golden):
+    g = golden("activation1d.npz")
+    f = golden("filters.npz")["aa12"]
+    y = O.activation1d(g["big_x"], g["big_alpha"], g["big_beta"], True, f, f)
+    np.testing.assert_allclose(y, g["big_y"], atol=2e-4, rtol=1e-5)  # sin of |arg| ~ 1e2 in fp32
+
+
+@pytest.mark.parametrize("tag", ["c8k3d1", "c8k7d3", "c6k11d5", "c4k11d5_short"])
+def test_conv1d(golden, tag):
+    g = golden("convs.npz")
+    c, k, d = g[tag + "_args"]
+    w = O.weight_norm_fold(g[tag + "_v"], g[tag + "_g"])
+    np.testing.assert_allclose(w, g[tag + "_w"], atol=1e-6, rtol=1e-6)
+    y = O.conv1d(g[tag + "_x"], w, g[tag + "_b"], int(d), O.get_padding(int(k), int(d)))
+    np.testing.assert_allclose(y, g[tag + "_y"], atol=5e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("tag", ["t8to4k8u4", "t6to3k4u2", "t4to2k16u8", "t4to2k4u2_len1"])
+def test_conv_transpose1d(golden, tag):
+    g = golden("convs.npz")
+    cin, cout, k, u = g[tag + "_args"]
+    w = O.weight_norm_fold(g[tag + "_v"], g[tag + "_g"])
+    np.testing.assert_allclose(w, g[tag + "_w"], atol=1e-6, rtol=1e-6)
+    y = O.conv_transpose1d(g[tag + "_x"], w, g[tag + "_b"], int(u), int(k - u) // 2)
+    assert y.shape == g[tag + "_y"].shape
+    np.testing.assert_allclose(y, g[tag + "_y"], atol=5e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("tag", list(TINY_VARIANTS))
+def test_tiny_generator(golden, tag):
+    g = golden("tiny_generator.npz")
+    cfg, sd = tiny_sd(tag)
+    y = O.generator_forward(sd, cfg, g[tag + "_mel"])
+    np.testing.assert_allclose(y, g[tag + "_y"], atol=2e-5)
+    y64 = O.generator_forward(sd, cfg, g[tag + "_mel"].astype(np.float64))
+    np.testing.assert_allclose(y64, g[tag + "_y_f64"], atol=1e-11)
+
+
+def test_synthesis_tail(golden):
+    g = golden("tiny_generator.npz")
+    cfg, sd = tiny_sd("b1_snakebeta_log")
+    mel = g["synth_mel"]
+    wav = O.generator_forward(sd, cfg, mel[None])[0, 0]
+    np.testing.assert_allclose(wav, g["voc_inf"][0], atol=2e-5)
+    audio = O.synthesis_tail(wav, mel.shape[-1], 8)
+    assert audio.shape == g["synth_audio"].shape and audio.dtype == np.float32
+    np.testing.assert_allclose(audio, g["synth_audio"], atol=2e-5)
+    assert audio[-1] == 0.0
+    with pytest.raises(ValueError):
+        O.synthesis_tail(wav[:80], 10, 8)  # fewer than 20 frames: the reference's broadcast fails too
+
+
+def test_unknown_activation_raises():
+    with pytest.raises(NotImplementedError):
+        synth.state_dict_spec(dict(TINY, activation="relu"))
+
+
+def test_repo_structure(golden):
+    g = golden("repo_generator.npz")
+    assert int(g["n_params"]) == 112_446_290 == synth.count_parameters(REPO)
+    assert int(g["n_tensors"]) == 784 == len(synth.state_dict_spec(REPO))
+    import hashlib
+    digest = hashlib.sha256("\n".join(f"{k}:{tuple(s)}" for k, (s, _) in synth.state_dict_spec(REPO).items()).encode()).digest()
+    assert bytes(g["keys_sha256"].tobytes()) == digest
+    v2 = dict(REPO, input_dim=128, upsample_rates=[8, 4, 2, 2, 2, 2], upsample_kernel_sizes=[16, 8, 4, 4, 4, 4])
+    assert int(golden("v2_generator.npz")["n_params"]) == 122_184_530 == synth.count_parameters(v2)
+
+
+def test_repo_generator_oracle(golden):
+    """Full-size repo generator, procedural checkpoint, fp32 oracle vs fp32 and fp64 reference."""
+    g = golden("repo_generator.npz")
+    sd = synth.synthetic_state_dict(REPO, seed=0)
+    y = O.generator_forward(sd, REPO, g["logmel_mel"])
+    assert y.shape == (1, 1, 24 * 256)
+    assert np.abs(y - g["logmel_y"]).max() < 2e-5
+    assert np.abs(y - g["logmel_y_f64"]).max() < 2e-5
