@@ -1,0 +1,215 @@
+/*
+ * bvg_b200.h -- C ABI of libbvg_b200.so: the B200 (sm_100a) BigVGAN vocoder kernels.
+ *
+ * The reference (WallaceRao/svc_inference_pipeline) has no FFI / plugin interface on this path:
+ * its boundary is three Python call sites (Generator(cfg.vocoder) modules/bigvgan.py:521,
+ * vocoder_model_loader utils/load_models.py:52-79, synthesis_audios modules/bigvgan_inference.py:29)
+ * and every arithmetic step is a PyTorch library call.  This header is therefore the interface the
+ * Python drop-in (svc_inference_pipeline_b200/modules/bigvgan.py) binds with ctypes; each entry point
+ * below cites the reference call it replaces.  See INTEGRATION.md for the binding stub.
+ *
+ * Conventions
+ *  - plain C types only; every pointer named d_* is a DEVICE pointer borrowed from the caller
+ *    (torch owns all memory; the library never allocates device memory);
+ *  - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *  - every function returns 0 on success, a negative BVG_E* code otherwise, and never throws;
+ *    bvg_last_error() returns a thread-local human-readable message for the last failure;
+ *  - activations are CHANNELS-LAST inside the library: [B, L, C] with C contiguous
+ *    (the reference's external layout [B, C, L] is converted by bvg_pack_mel / produced by
+ *    bvg_post_fwd);
+ *  - element formats (bvg_dtype): F32, BF16, or SPLIT = two bf16 planes (hi, lo) with
+ *    hi = bf16(x), lo = bf16(x - hi); SPLIT operands feed the 3-MMA error-compensated
+ *    tensor-core product (hi*hi + hi*lo + lo*hi, fp32 accumulate) of the fp32-parity path.
+ */
+#ifndef BVG_B200_H_
+#define BVG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BVG_ABI_VERSION 1
+
+enum bvg_status {
+  BVG_OK = 0,
+  BVG_EINVAL = -1,   /* bad argument / unsupported shape */
+  BVG_ECUDA = -2,    /* CUDA runtime or driver error (message has the CUDA string) */
+  BVG_EARCH = -3,    /* device is not sm_100 */
+  BVG_ENOMEM = -4    /* caller-provided buffer too small */
+};
+
+enum bvg_dtype { BVG_F32 = 0, BVG_BF16 = 1, BVG_SPLIT = 2 };
+enum bvg_act { BVG_SNAKE = 0, BVG_SNAKEBETA = 1 };
+enum bvg_backend {
+  BVG_SIMT = 0, /* fp32 FFMA implicit GEMM on CUDA cores: exact-fp32 anchor path */
+  BVG_UMMA = 1  /* tcgen05.mma + TMEM accumulators fed by TMA (bf16 operands, fp32 accumulate) */
+};
+
+/* A tensor handed to a kernel: base pointer(s) + element format.  `lo` is only read for SPLIT. */
+typedef struct bvg_tensor {
+  void* d_ptr;  /* F32: float*, BF16: bf16*, SPLIT: bf16* hi plane */
+  void* d_lo;   /* SPLIT: bf16* lo plane, else NULL */
+  int32_t dtype; /* bvg_dtype */
+  int32_t _pad;
+} bvg_tensor;
+
+/* ------------------------------------------------------------------------------------------
+ * Fused anti-aliased activation  (replaces Activation1d.forward, modules/bigvgan.py:251-256:
+ * UpSample1d :278-287 -> Snake/SnakeBeta :84-95/:146-159 -> DownSample1d :304-307 / :224-231).
+ * One kernel; the 2x-rate signal lives only in registers.
+ *   y[b,t,c] = sum_k f[k] * s[clamp(2t+k-5)],  s = snake(u),  u = 2x polyphase upsample of x.
+ * d_a[c]   = exp(alpha[c]) (or alpha[c] for linear scale);  d_invb[c] = 1/(b[c] + 1e-9)
+ * with b = beta (snakebeta) or alpha (snake), exponentiated likewise: precomputed at load.
+ * x: F32 or BF16 [B,L,C];  y: F32, BF16 or SPLIT [B,L,C].  taps: the 12 filter taps (host).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct bvg_amp_desc {
+  bvg_tensor x;
+  bvg_tensor y;
+  const float* d_a;
+  const float* d_invb;
+  float taps_up[12];   /* upsample.filter   (state_dict buffer, modules/bigvgan.py:273-276) */
+  float taps_down[12]; /* downsample.lowpass.filter (modules/bigvgan.py:220-221) */
+  int32_t B, L, C;
+  int32_t fast_sin;    /* 1: MUFU sin (bf16 path); 0: range-reduced polynomial (fp32 path) */
+} bvg_amp_desc;
+
+int bvg_amp_fwd(const bvg_amp_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense convolution as a "tap GEMM"  (replaces the weight-normed Conv1d of AMPBlock1/2,
+ * modules/bigvgan.py:319-386 / :428-431, conv_pre :529-537 / :602, and the ConvTranspose1d
+ * upsamplers :547-561 / :607):
+ *   out[b, t, n] = epi( bias[n] + sum_{tap} sum_{ci} x[b, t + shift[tile(n)][tap], ci] * W[n][tap][ci] )
+ * rows of x outside [0, L) read as zero (Conv1d zero padding; ConvTranspose1d has no such taps).
+ * Conv1d(k, dilation d): N = Cout, shifts (j - (k-1)/2) * d.  ConvTranspose1d(k, stride u):
+ * N = u*Cout (phase-major), out viewed as [B, L, u*Cout] == [B, L*u, Cout]; each phase uses the
+ * input shifts its taps touch.  epi: + res, + acc_in, / div, store in out.dtype.
+ * Weights are pre-folded (w = g*v/||v||, torch.nn.utils.weight_norm) and pre-packed by
+ * bvg_pack_conv_weights into the layout of the chosen backend.
+ * ------------------------------------------------------------------------------------------ */
+#define BVG_MAX_TAPS 16
+#define BVG_MAX_NTILES 32  /* UMMA tiles with their own tap table; SIMT uses entry 0 for all tiles */
+
+typedef struct bvg_conv_weights {
+  int32_t backend;     /* bvg_backend */
+  int32_t cin;         /* input channels (GEMM K per tap) */
+  int32_t n_total;     /* GEMM N: Cout (conv) or u*Cout (transposed conv) */
+  int32_t n_tile;      /* N-tile the packing was made for (UMMA: multiple of 16, <= 256) */
+  int32_t n_tiles;
+  int32_t cin_pad;     /* K extent of the packed weights: SIMT round_up(cin,4), UMMA round_up(cin,64) */
+  int32_t x_pitch;     /* channel pitch the x tensor must have: SIMT round_up(cin,4), UMMA round_up(cin,8) */
+  int32_t tap_stride;  /* tap slots reserved per N tile in the packed planes (>= max n_taps) */
+  int32_t split;       /* UMMA: 1 = hi and lo planes packed (fp32-parity path) */
+  int32_t n_taps[BVG_MAX_NTILES];                  /* taps of each N tile */
+  int32_t shift[BVG_MAX_NTILES][BVG_MAX_TAPS];    /* input row shift of each tap */
+  void* d_w;           /* SIMT: float [tile][tap][cin_pad][n_tile]; UMMA: bf16 [tile][tap][n_tile][cin_pad] */
+  void* d_w_lo;        /* UMMA split: lo plane, same layout */
+  const float* d_bias; /* [n_total] */
+} bvg_conv_weights;
+
+typedef struct bvg_conv_desc {
+  bvg_tensor x;        /* [B, L, cin]   SIMT: F32;  UMMA: BF16 or SPLIT */
+  bvg_tensor out;      /* [B, L, n_total] */
+  bvg_tensor res;      /* optional residual, same shape as out (d_ptr NULL = none); F32 or BF16 */
+  bvg_tensor acc_in;   /* optional running sum to add (xs += ...), same shape; F32 or BF16 */
+  float div;           /* out /= div when != 1 (the xs / num_kernels of modules/bigvgan.py:615) */
+  int32_t B, L;
+  const bvg_conv_weights* w;
+} bvg_conv_desc;
+
+int bvg_conv_fwd(const bvg_conv_desc* d, void* stream);
+
+/* Weight-norm fold + pack (replaces the per-forward torch._weight_norm pre-hook, i.e.
+ * torch.nn.utils.weight_norm at modules/bigvgan.py:319-386,529,550,593: done once at load).
+ *   d_v: weight_v  Conv1d [Cout, Cin, K]   / ConvTranspose1d [Cin, Cout, K]
+ *   d_g: weight_g  [dim0,1,1] or NULL when d_v already holds the folded weight
+ * Fills w->n_taps/shift/cin_pad/n_tiles and writes the packed planes into w->d_w (/d_w_lo)
+ * and the phase-replicated bias into d_bias_out.  Query sizes first with bvg_conv_pack_bytes. */
+typedef struct bvg_conv_geom {
+  int32_t transposed;  /* 0: Conv1d, 1: ConvTranspose1d */
+  int32_t cin, cout, ksize;
+  int32_t dilation;    /* Conv1d */
+  int32_t stride;      /* ConvTranspose1d upsampling rate u */
+  int32_t padding;     /* Conv1d: get_padding(k, d); ConvTranspose1d: (k - u) / 2 */
+  int32_t backend;     /* bvg_backend */
+  int32_t split;       /* UMMA only */
+  int32_t n_tile;      /* 0 = choose */
+} bvg_conv_geom;
+
+int bvg_conv_pack_bytes(const bvg_conv_geom* g, size_t* weight_plane_bytes, size_t* bias_bytes);
+int bvg_conv_geometry(const bvg_conv_geom* g, bvg_conv_weights* w); /* host only: tiling + tap tables */
+/* d_scratch: >= max(cin, cout) floats of device scratch (per-slice g/||v||). */
+int bvg_pack_conv_weights(const bvg_conv_geom* g, const float* d_v, const float* d_g, const float* d_bias,
+                          bvg_conv_weights* w, float* d_bias_out, float* d_scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Tail: conv_post (Conv1d C->1, k=7, pad 3) + tanh  (modules/bigvgan.py:593, :619-620).
+ * x: F32 or BF16 [B, L, C];  d_w: float [7][C] folded;  d_out: float [B, L] (== [B,1,L]).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct bvg_post_desc {
+  bvg_tensor x;
+  const float* d_w;
+  float bias;
+  float* d_out;
+  int32_t B, L, C, ksize;
+} bvg_post_desc;
+
+int bvg_post_fwd(const bvg_post_desc* d, void* stream);
+int bvg_pack_post_weights(const float* d_v, const float* d_g, int32_t cin, int32_t ksize, float* d_w_out,
+                          float* d_scratch /* >= 1 float */, void* stream);
+
+/* Head: mel [B, C, T] float (reference layout, modules/bigvgan.py:600) -> channels-last operand
+ * [B, T, c_pad] (F32, BF16 or SPLIT), zero-filling channels C..c_pad-1. */
+typedef struct bvg_pack_desc {
+  const float* d_mel;
+  bvg_tensor out;
+  int32_t B, C, T, c_pad;
+} bvg_pack_desc;
+
+int bvg_pack_mel(const bvg_pack_desc* d, void* stream);
+
+/* Layout/format helpers used by tests and by the sharded stitch. */
+int bvg_convert(const bvg_tensor* src, const bvg_tensor* dst, size_t n_elems, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Programs: a whole Generator.forward (modules/bigvgan.py:600-622) as one pre-validated launch
+ * list, so the per-call host work is one C call (and the list can be captured in a CUDA graph).
+ * ------------------------------------------------------------------------------------------ */
+enum bvg_op_kind { BVG_OP_PACK = 0, BVG_OP_AMP = 1, BVG_OP_CONV = 2, BVG_OP_POST = 3 };
+
+typedef struct bvg_op {
+  int32_t kind; /* bvg_op_kind */
+  int32_t _pad;
+  union {
+    bvg_pack_desc pack;
+    bvg_amp_desc amp;
+    bvg_conv_desc conv;
+    bvg_post_desc post;
+  } u;
+} bvg_op;
+
+typedef struct bvg_program bvg_program;
+
+int bvg_program_create(const bvg_op* ops, int32_t n_ops, bvg_program** out);
+int bvg_program_run(bvg_program* p, void* stream);
+/* Same launches with a CUDA event between consecutive ops; synchronises the stream and returns the
+ * device time (ms) and launch count per bvg_op_kind (arrays of 4).  Measurement aid for bench.py. */
+int bvg_program_run_timed(bvg_program* p, void* stream, float* ms_by_kind, int32_t* n_by_kind);
+int bvg_program_num_launches(const bvg_program* p);
+void bvg_program_destroy(bvg_program* p);
+
+/* Misc */
+int bvg_abi_version(void);
+const char* bvg_last_error(void);
+int bvg_device_check(int device); /* BVG_OK iff `device` is compute capability 10.x */
+int bvg_set_tuning(const char* name, int value); /* test / tuning knobs: amp_vec, amp_chunk, umma_a_mode, umma_desc_mode, umma_max_ctas */
+size_t bvg_sizeof_op(void);       /* ABI self-check for the ctypes mirror */
+size_t bvg_sizeof_conv_weights(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BVG_B200_H_ */

@@ -1,0 +1,203 @@
+"""ctypes binding of ``libbvg_b200.so`` (C ABI: ``include/bvg_b200.h``).
+
+The library is the product's only compute path: if it is missing or the device is not sm_100,
+loading / calling fails loudly -- there is no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbvg_b200.so")
+
+F32, BF16, SPLIT = 0, 1, 2
+SIMT, UMMA = 0, 1
+OP_PACK, OP_AMP, OP_CONV, OP_POST = 0, 1, 2, 3
+MAX_TAPS, MAX_NTILES = 16, 32
+
+
+class BvgError(RuntimeError):
+    pass
+
+
+class Tensor(C.Structure):
+    _fields_ = [("d_ptr", C.c_void_p), ("d_lo", C.c_void_p), ("dtype", C.c_int32), ("_pad", C.c_int32)]
+
+
+class AmpDesc(C.Structure):
+    _fields_ = [
+        ("x", Tensor),
+        ("y", Tensor),
+        ("d_a", C.c_void_p),
+        ("d_invb", C.c_void_p),
+        ("taps_up", C.c_float * 12),
+        ("taps_down", C.c_float * 12),
+        ("B", C.c_int32),
+        ("L", C.c_int32),
+        ("C", C.c_int32),
+        ("fast_sin", C.c_int32),
+    ]
+
+
+class ConvWeights(C.Structure):
+    _fields_ = [
+        ("backend", C.c_int32),
+        ("cin", C.c_int32),
+        ("n_total", C.c_int32),
+        ("n_tile", C.c_int32),
+        ("n_tiles", C.c_int32),
+        ("cin_pad", C.c_int32),
+        ("x_pitch", C.c_int32),
+        ("tap_stride", C.c_int32),
+        ("split", C.c_int32),
+        ("n_taps", C.c_int32 * MAX_NTILES),
+        ("shift", (C.c_int32 * MAX_TAPS) * MAX_NTILES),
+        ("d_w", C.c_void_p),
+        ("d_w_lo", C.c_void_p),
+        ("d_bias", C.c_void_p),
+    ]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("x", Tensor),
+        ("out", Tensor),
+        ("res", Tensor),
+        ("acc_in", Tensor),
+        ("div", C.c_float),
+        ("B", C.c_int32),
+        ("L", C.c_int32),
+        ("w", C.POINTER(ConvWeights)),
+    ]
+
+
+class ConvGeom(C.Structure):
+    _fields_ = [
+        ("transposed", C.c_int32),
+        ("cin", C.c_int32),
+        ("cout", C.c_int32),
+        ("ksize", C.c_int32),
+        ("dilation", C.c_int32),
+        ("stride", C.c_int32),
+        ("padding", C.c_int32),
+        ("backend", C.c_int32),
+        ("split", C.c_int32),
+        ("n_tile", C.c_int32),
+    ]
+
+
+class PostDesc(C.Structure):
+    _fields_ = [
+        ("x", Tensor),
+        ("d_w", C.c_void_p),
+        ("bias", C.c_float),
+        ("d_out", C.c_void_p),
+        ("B", C.c_int32),
+        ("L", C.c_int32),
+        ("C", C.c_int32),
+        ("ksize", C.c_int32),
+    ]
+
+
+class PackDesc(C.Structure):
+    _fields_ = [
+        ("d_mel", C.c_void_p),
+        ("out", Tensor),
+        ("B", C.c_int32),
+        ("C", C.c_int32),
+        ("T", C.c_int32),
+        ("c_pad", C.c_int32),
+    ]
+
+
+class _OpUnion(C.Union):
+    _fields_ = [("pack", PackDesc), ("amp", AmpDesc), ("conv", ConvDesc), ("post", PostDesc)]
+
+
+class Op(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("u", _OpUnion)]
+
+
+_lib = None
+
+# every symbol include/bvg_b200.h declares (checked by tests/test_capi_symbols.py)
+EXPORTS = [
+    "bvg_abi_version",
+    "bvg_last_error",
+    "bvg_device_check",
+    "bvg_sizeof_op",
+    "bvg_sizeof_conv_weights",
+    "bvg_amp_fwd",
+    "bvg_conv_fwd",
+    "bvg_conv_geometry",
+    "bvg_conv_pack_bytes",
+    "bvg_pack_conv_weights",
+    "bvg_post_fwd",
+    "bvg_pack_post_weights",
+    "bvg_pack_mel",
+    "bvg_convert",
+    "bvg_program_create",
+    "bvg_program_run",
+    "bvg_program_run_timed",
+    "bvg_set_tuning",
+    "bvg_program_num_launches",
+    "bvg_program_destroy",
+]
+
+
+def lib():
+    """Load (once) and return the shared library; raises BvgError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BvgError(
+            f"{LIB_PATH} not found: build it with `make -C svc_inference_pipeline_b200/csrc -j` "
+            "(or `python -c 'import __graft_entry__ as g; g.build()'`). There is no fallback path."
+        )
+    L = C.CDLL(LIB_PATH)
+    L.bvg_last_error.restype = C.c_char_p
+    L.bvg_sizeof_op.restype = C.c_size_t
+    L.bvg_sizeof_conv_weights.restype = C.c_size_t
+    L.bvg_abi_version.restype = C.c_int
+    for name, argtypes in {
+        "bvg_device_check": [C.c_int],
+        "bvg_set_tuning": [C.c_char_p, C.c_int],
+        "bvg_amp_fwd": [C.POINTER(AmpDesc), C.c_void_p],
+        "bvg_conv_fwd": [C.POINTER(ConvDesc), C.c_void_p],
+        "bvg_post_fwd": [C.POINTER(PostDesc), C.c_void_p],
+        "bvg_pack_mel": [C.POINTER(PackDesc), C.c_void_p],
+        "bvg_convert": [C.POINTER(Tensor), C.POINTER(Tensor), C.c_size_t, C.c_void_p],
+        "bvg_conv_geometry": [C.POINTER(ConvGeom), C.POINTER(ConvWeights)],
+        "bvg_conv_pack_bytes": [C.POINTER(ConvGeom), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)],
+        "bvg_pack_conv_weights": [C.POINTER(ConvGeom), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(ConvWeights), C.c_void_p, C.c_void_p, C.c_void_p],
+        "bvg_pack_post_weights": [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p],
+        "bvg_program_create": [C.POINTER(Op), C.c_int32, C.POINTER(C.c_void_p)],
+        "bvg_program_run": [C.c_void_p, C.c_void_p],
+        "bvg_program_run_timed": [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)],
+        "bvg_program_num_launches": [C.c_void_p],
+        "bvg_program_destroy": [C.c_void_p],
+    }.items():
+        fn = getattr(L, name)
+        fn.argtypes = argtypes
+        fn.restype = None if name == "bvg_program_destroy" else C.c_int
+    if L.bvg_abi_version() != 1:
+        raise BvgError(f"ABI mismatch: library reports version {L.bvg_abi_version()}, binding expects 1")
+    if L.bvg_sizeof_op() != C.sizeof(Op) or L.bvg_sizeof_conv_weights() != C.sizeof(ConvWeights):
+        raise BvgError(
+            f"struct layout mismatch: C sizeof(bvg_op)={L.bvg_sizeof_op()} vs ctypes {C.sizeof(Op)}; "
+            f"sizeof(bvg_conv_weights)={L.bvg_sizeof_conv_weights()} vs ctypes {C.sizeof(ConvWeights)}"
+        )
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().bvg_last_error().decode("utf-8", "replace")
+        raise BvgError(f"{what or 'libbvg_b200'} failed (code {rc}): {msg}")
+
+
+def set_tuning(name: str, value: int) -> None:
+    check(lib().bvg_set_tuning(name.encode(), int(value)), f"set_tuning({name})")

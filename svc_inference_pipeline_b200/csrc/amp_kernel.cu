@@ -1,0 +1,311 @@
+// K-A: fused anti-aliased activation (Activation1d) for channels-last [B, L, C] tensors.
+//
+// Replaces reference modules/bigvgan.py:251-256 (UpSample1d :278-287 -> Snake/SnakeBeta
+// :84-95 / :146-159 -> DownSample1d :304-307 -> LowPassFilter1d :224-231): one pass over HBM,
+// the 2x-rate signal never leaves registers.
+//
+// Math (pinned by tests/golden/activation1d.npz):
+//   u[2i]   = sum_m g[2m+1] x[clamp(i+2-m)],  u[2i+1] = sum_m g[2m] x[clamp(i+3-m)],  g = 2*f_up
+//   s[j]    = u[j] + invb * sin^2(a * u[j])
+//   z[t]    = sum_k f_down[k] * s[clamp(2t + k - 5, 0, 2L-1)]
+// Two different replicate clamps: on x (1x rate) and on the *activated* s (2x rate).
+//
+// Work decomposition: one thread owns VEC adjacent channels and a run of TT consecutive time
+// steps.  It slides along time keeping the 6-row x window and the 12-value s window in
+// registers; every step consumes one new x row and produces two new s values and one output
+// row.  Steps are processed in blocks of 6 with two register sets used ping-pong, so the
+// windows rotate with compile-time indices and no register moves.  A warp covers 32*VEC
+// adjacent channels of one row => every global access is a fully coalesced row segment.
+#include "common.cuh"
+
+namespace bvg {
+
+struct AmpParams {
+  const void* x;
+  void* y;
+  void* y_lo;
+  const float* a;
+  const float* invb;
+  float gu[12];  // 2 * upsample taps (the ratio gain of bigvgan.py:282 folded in; exact, power of two)
+  float fd[12];  // downsample taps
+  int B, L, C;
+  int CG;       // channel groups = C / VEC
+  int nchunks;  // time chunks per batch item
+  int nblk2;    // chunk length = 12 * nblk2 steps
+  long long total_threads;
+};
+
+template <bool IN_BF16, int VEC>
+__device__ __forceinline__ void load_row(const void* base, long long off, float (&v)[VEC]) {
+  if constexpr (!IN_BF16) {
+    const float* p = reinterpret_cast<const float*>(base) + off;
+    if constexpr (VEC == 4) {
+      float4 t = __ldg(reinterpret_cast<const float4*>(p));
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else if constexpr (VEC == 2) {
+      float2 t = __ldg(reinterpret_cast<const float2*>(p));
+      v[0] = t.x; v[1] = t.y;
+    } else {
+      v[0] = __ldg(p);
+    }
+  } else {
+    const uint16_t* p = reinterpret_cast<const uint16_t*>(base) + off;
+    if constexpr (VEC == 4) {
+      uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+      unpack_bf16x2(t.x, v[0], v[1]);
+      unpack_bf16x2(t.y, v[2], v[3]);
+    } else if constexpr (VEC == 2) {
+      uint32_t t = __ldg(reinterpret_cast<const uint32_t*>(p));
+      unpack_bf16x2(t, v[0], v[1]);
+    } else {
+      v[0] = bf16_bits_to_float(__ldg(p));
+    }
+  }
+}
+
+template <int VEC>
+__device__ __forceinline__ void store_bf16_row(void* base, long long off, const float (&v)[VEC]) {
+  uint16_t* p = reinterpret_cast<uint16_t*>(base) + off;
+  if constexpr (VEC == 4) {
+    uint2 t;
+    t.x = pack_bf16x2(v[0], v[1]);
+    t.y = pack_bf16x2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = t;
+  } else if constexpr (VEC == 2) {
+    *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(v[0], v[1]);
+  } else {
+    *p = (uint16_t)float_to_bf16_bits(v[0]);
+  }
+}
+
+template <int OUT_MODE, int VEC>
+__device__ __forceinline__ void store_row(void* y, void* y_lo, long long off, const float (&v)[VEC]) {
+  if constexpr (OUT_MODE == BVG_F32) {
+    float* p = reinterpret_cast<float*>(y) + off;
+    if constexpr (VEC == 4) {
+      *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    } else if constexpr (VEC == 2) {
+      *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+    } else {
+      *p = v[0];
+    }
+  } else if constexpr (OUT_MODE == BVG_BF16) {
+    store_bf16_row<VEC>(y, off, v);
+  } else {
+    float hi[VEC], lo[VEC];
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) split_bf16(v[c], hi[c], lo[c]);
+    store_bf16_row<VEC>(y, off, hi);
+    store_bf16_row<VEC>(y_lo, off, lo);
+  }
+}
+
+// sin(a*u): FAST = MUFU on the raw product (phase error ~|a*u| * 1e-7, like the reference's own
+// fp32 rounding of a*u); otherwise reduce exactly to [-pi/2, pi/2] first (sin^2 has period pi),
+// which keeps MUFU.SIN in its most accurate range (abs err 2^-21).  apar = a (FAST) or a/pi.
+template <bool FAST_SIN>
+__device__ __forceinline__ float snake_one(float u, float apar, float invb) {
+  float s;
+  if constexpr (FAST_SIN) {
+    s = __sinf(u * apar);
+  } else {
+    float t = u * apar;               // half-turns
+    float k = (t + 12582912.0f) - 12582912.0f;  // rint for |t| < 2^22
+    float r = t - k;                  // [-0.5, 0.5]
+    s = __sinf(r * 3.14159265358979f);
+  }
+  return fmaf(invb, s * s, u);
+}
+
+template <bool IN_BF16, int OUT_MODE, int VEC, bool FAST_SIN, bool STORE>
+__device__ __forceinline__ void amp_block6(const AmpParams& p, const float (&xa)[6][VEC], float (&xb)[6][VEC],
+                                           const float (&sa)[12][VEC], float (&sb)[12][VEC], int tau0, long long in_base,
+                                           long long out_base, const float (&apar)[VEC], const float (&invb)[VEC]) {
+  const int L = p.L;
+  // rows x[tau0+6 .. tau0+11] feed the *next* block; issue them first so they are in flight
+  // while this block computes.
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    int r = min(max(tau0 + 6 + j, 0), L - 1);
+    load_row<IN_BF16, VEC>(p.x, in_base + (long long)r * p.C, xb[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    float pa[VEC], pb[VEC];
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) pa[c] = pb[c] = 0.f;
+#pragma unroll
+    for (int m = 0; m < 6; ++m) {
+      const int w = j + 5 - m;  // window slot of x[tau + 5 - m]
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) {
+        const float xv = (w < 6) ? xa[w < 6 ? w : 0][c] : xb[w >= 6 ? w - 6 : 0][c];
+        pb[c] = fmaf(p.gu[2 * m + 1], xv, pb[c]);  // s[2 tau + 6]: even phase, i = tau + 3
+        pa[c] = fmaf(p.gu[2 * m], xv, pa[c]);      // s[2 tau + 5]: odd phase,  i = tau + 2
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) {
+      pa[c] = snake_one<FAST_SIN>(pa[c], apar[c], invb[c]);
+      pb[c] = snake_one<FAST_SIN>(pb[c], apar[c], invb[c]);
+    }
+    const int tau = tau0 + j;
+    if (tau >= L - 3) {  // right replicate clamp of the activated signal: s[j > 2L-1] = s[2L-1]
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) {
+        const float prev = (j == 0) ? sa[11][c] : sb[j == 0 ? 0 : 2 * j - 1][c];
+        if (tau >= L - 2) pa[c] = prev;
+        pb[c] = pa[c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) {
+      sb[2 * j][c] = pa[c];
+      sb[2 * j + 1][c] = pb[c];
+    }
+    if constexpr (STORE) {
+      float z[VEC];
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) z[c] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        const int i = 2 * j + 2 + k;  // slot in (sa ++ sb) of s[2 tau - 5 + k]
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) {
+          const float sv = (i < 12) ? sa[i < 12 ? i : 0][c] : sb[i >= 12 ? i - 12 : 0][c];
+          z[c] = fmaf(p.fd[k], sv, z[c]);
+        }
+      }
+      if (tau < L) store_row<OUT_MODE, VEC>(p.y, p.y_lo, out_base + (long long)tau * p.C, z);
+    }
+  }
+}
+
+template <bool IN_BF16, int OUT_MODE, int VEC, bool FAST_SIN>
+__global__ void __launch_bounds__(128) amp_kernel(const __grid_constant__ AmpParams p) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= p.total_threads) return;
+  const int cg = (int)(tid % p.CG);
+  const long long rest = tid / p.CG;
+  const int chunk = (int)(rest % p.nchunks);
+  const int b = (int)(rest / p.nchunks);
+  const int TT = 12 * p.nblk2;
+  const int t0 = chunk * TT;
+  const int L = p.L;
+  const long long base = (long long)b * L * p.C + (long long)cg * VEC;
+
+  float apar[VEC], invb[VEC];
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) {
+    const float a = __ldg(p.a + cg * VEC + c);
+    apar[c] = FAST_SIN ? a : a * 0.318309886183790672f;
+    invb[c] = __ldg(p.invb + cg * VEC + c);
+  }
+
+  float xa[6][VEC], xb[6][VEC], sa[12][VEC], sb[12][VEC];
+#pragma unroll
+  for (int k = 0; k < 12; ++k)
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) sa[k][c] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    int r = min(max(t0 - 6 + k, 0), L - 1);
+    load_row<IN_BF16, VEC>(p.x, base + (long long)r * p.C, xa[k]);
+  }
+  // warm-up block (tau = t0-6 .. t0-1): fills sb = s[2 t0 - 7 .. 2 t0 + 4], no output
+  amp_block6<IN_BF16, OUT_MODE, VEC, FAST_SIN, false>(p, xa, xb, sa, sb, t0 - 6, base, base, apar, invb);
+  if (t0 == 0) {  // left replicate clamp of the activated signal: s[j < 0] = s[0] (slot 7)
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) sb[k][c] = sb[7][c];
+  }
+  int t = t0;
+  for (int i = 0; i < p.nblk2; ++i) {
+    if (t >= L) break;
+    amp_block6<IN_BF16, OUT_MODE, VEC, FAST_SIN, true>(p, xb, xa, sb, sa, t, base, base, apar, invb);
+    t += 6;
+    if (t >= L) break;
+    amp_block6<IN_BF16, OUT_MODE, VEC, FAST_SIN, true>(p, xa, xb, sa, sb, t, base, base, apar, invb);
+    t += 6;
+  }
+}
+
+template <bool IN_BF16, int OUT_MODE, int VEC, bool FAST_SIN>
+static cudaError_t launch_amp(const AmpParams& p, cudaStream_t st) {
+  const int threads = 128;
+  const long long blocks = ceil_div_ll(p.total_threads, threads);
+  amp_kernel<IN_BF16, OUT_MODE, VEC, FAST_SIN><<<(unsigned)blocks, threads, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <bool IN_BF16, int OUT_MODE, int VEC>
+static cudaError_t launch_amp_sin(const AmpParams& p, bool fast, cudaStream_t st) {
+  return fast ? launch_amp<IN_BF16, OUT_MODE, VEC, true>(p, st) : launch_amp<IN_BF16, OUT_MODE, VEC, false>(p, st);
+}
+
+template <int VEC>
+static cudaError_t launch_amp_vec(const AmpParams& p, bool in_bf16, int out_mode, bool fast, cudaStream_t st) {
+  if (in_bf16) {
+    if (out_mode == BVG_F32) return launch_amp_sin<true, BVG_F32, VEC>(p, fast, st);
+    if (out_mode == BVG_BF16) return launch_amp_sin<true, BVG_BF16, VEC>(p, fast, st);
+    return launch_amp_sin<true, BVG_SPLIT, VEC>(p, fast, st);
+  }
+  if (out_mode == BVG_F32) return launch_amp_sin<false, BVG_F32, VEC>(p, fast, st);
+  if (out_mode == BVG_BF16) return launch_amp_sin<false, BVG_BF16, VEC>(p, fast, st);
+  return launch_amp_sin<false, BVG_SPLIT, VEC>(p, fast, st);
+}
+
+int amp_vec_override = 0;  // test/tuning hook: force VEC (set through bvg_set_tuning)
+int amp_chunk_override = 0;
+
+int amp_forward(const bvg_amp_desc* d, cudaStream_t st) {
+  BVG_REQUIRE(d != nullptr, "amp: null descriptor");
+  BVG_REQUIRE(d->B > 0 && d->L > 0 && d->C > 0, "amp: bad shape B=%d L=%d C=%d", d->B, d->L, d->C);
+  BVG_REQUIRE(d->x.d_ptr && d->y.d_ptr && d->d_a && d->d_invb, "amp: null pointer");
+  BVG_REQUIRE(d->x.dtype == BVG_F32 || d->x.dtype == BVG_BF16, "amp: input must be F32 or BF16");
+  BVG_REQUIRE(d->y.dtype >= BVG_F32 && d->y.dtype <= BVG_SPLIT, "amp: bad output dtype");
+  BVG_REQUIRE(d->y.dtype != BVG_SPLIT || d->y.d_lo, "amp: SPLIT output needs a lo plane");
+  BVG_REQUIRE((long long)d->L * d->C < (1ll << 31), "amp: L*C too large for one batch item");
+
+  int vec = (d->C % 4 == 0) ? 4 : (d->C % 2 == 0 ? 2 : 1);
+  if (amp_vec_override && d->C % amp_vec_override == 0) vec = amp_vec_override;
+
+  AmpParams p;
+  p.x = d->x.d_ptr;
+  p.y = d->y.d_ptr;
+  p.y_lo = d->y.d_lo;
+  p.a = d->d_a;
+  p.invb = d->d_invb;
+  for (int k = 0; k < 12; ++k) {
+    p.gu[k] = 2.0f * d->taps_up[k];
+    p.fd[k] = d->taps_down[k];
+  }
+  p.B = d->B;
+  p.L = d->L;
+  p.C = d->C;
+  p.CG = d->C / vec;
+  // chunk length: as long as possible (6 warm-up steps per chunk are recomputed work) while
+  // still giving the machine several full waves of threads
+  int nblk2 = 8;
+  const long long want = 148ll * 2048 * 2;
+  while (nblk2 > 1 && (long long)d->B * p.CG * ceil_div(d->L, 12 * nblk2) < want) nblk2 >>= 1;
+  if (amp_chunk_override > 0) nblk2 = amp_chunk_override;
+  p.nblk2 = nblk2;
+  p.nchunks = ceil_div(d->L, 12 * nblk2);
+  p.total_threads = (long long)d->B * p.nchunks * p.CG;
+  BVG_REQUIRE(ceil_div_ll(p.total_threads, 128) < (1ll << 31), "amp: grid too large");
+
+  cudaError_t e;
+  const bool in_bf16 = d->x.dtype == BVG_BF16;
+  if (vec == 4)
+    e = launch_amp_vec<4>(p, in_bf16, d->y.dtype, d->fast_sin != 0, st);
+  else if (vec == 2)
+    e = launch_amp_vec<2>(p, in_bf16, d->y.dtype, d->fast_sin != 0, st);
+  else
+    e = launch_amp_vec<1>(p, in_bf16, d->y.dtype, d->fast_sin != 0, st);
+  if (e != cudaSuccess) return cuda_fail(e, "amp_kernel launch");
+  return BVG_OK;
+}
+
+}  // namespace bvg

@@ -1,0 +1,238 @@
+// extern "C" surface of libbvg_b200.so (see include/bvg_b200.h) and the program runner.
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace bvg {
+
+// ---- error plumbing -------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return BVG_ECUDA;
+}
+
+// kernels (defined in the other translation units)
+int amp_forward(const bvg_amp_desc* d, cudaStream_t st);
+int conv_simt_forward(const bvg_conv_desc* d, cudaStream_t st);
+int conv_umma_forward(const bvg_conv_desc* d, cudaStream_t st);
+int post_forward(const bvg_post_desc* d, cudaStream_t st);
+int pack_mel(const bvg_pack_desc* d, cudaStream_t st);
+int convert(const bvg_tensor* src, const bvg_tensor* dst, size_t n, cudaStream_t st);
+int conv_geometry(const bvg_conv_geom* g, bvg_conv_weights* w);
+size_t conv_plane_elems(const bvg_conv_weights* w);
+int pack_conv_weights(const bvg_conv_geom* g, const float* d_v, const float* d_g, const float* d_bias, bvg_conv_weights* w, float* d_bias_out,
+                      float* d_scale_scratch, cudaStream_t st);
+int pack_post_weights(const float* d_v, const float* d_g, int cin, int ksize, float* d_w_out, float* d_scale_scratch, cudaStream_t st);
+
+struct UmmaLaunch;
+int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out);
+int conv_umma_launch(const UmmaLaunch* l, cudaStream_t st);
+size_t umma_launch_size();
+extern int amp_vec_override, amp_chunk_override, umma_a_mode, umma_desc_mode, umma_max_ctas;
+
+static int conv_forward(const bvg_conv_desc* d, cudaStream_t st) {
+  BVG_REQUIRE(d && d->w, "conv: null descriptor");
+  if (d->w->backend == BVG_SIMT) return conv_simt_forward(d, st);
+  if (d->w->backend == BVG_UMMA) return conv_umma_forward(d, st);
+  set_error("conv: unknown backend %d", d->w->backend);
+  return BVG_EINVAL;
+}
+
+}  // namespace bvg
+
+// A program owns deep copies of its op descriptors (and of the weight descriptors they point
+// to), plus the pre-encoded TMA launch records of its tensor-core ops.
+struct bvg_program {
+  std::vector<bvg_op> ops;
+  std::vector<bvg_conv_weights*> owned_weights;
+  std::vector<void*> umma;  // UmmaLaunch* per op (nullptr for the others)
+  int launches = 0;
+  ~bvg_program() {
+    for (auto* w : owned_weights) delete w;
+    for (auto* u : umma) ::operator delete(u);
+  }
+};
+
+extern "C" {
+
+int bvg_abi_version(void) { return BVG_ABI_VERSION; }
+const char* bvg_last_error(void) { return bvg::g_err; }
+size_t bvg_sizeof_op(void) { return sizeof(bvg_op); }
+size_t bvg_sizeof_conv_weights(void) { return sizeof(bvg_conv_weights); }
+
+int bvg_device_check(int device) {
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return bvg::cuda_fail(e, "cudaGetDeviceProperties");
+  if (prop.major != 10) {
+    bvg::set_error("device %d is sm_%d%d; libbvg_b200 is built for sm_100a only (no fallback)", device, prop.major, prop.minor);
+    return BVG_EARCH;
+  }
+  return BVG_OK;
+}
+
+int bvg_set_tuning(const char* name, int value) {
+  if (!name) return BVG_EINVAL;
+  if (!strcmp(name, "amp_vec")) bvg::amp_vec_override = value;
+  else if (!strcmp(name, "amp_chunk")) bvg::amp_chunk_override = value;
+  else if (!strcmp(name, "umma_a_mode")) bvg::umma_a_mode = value;
+  else if (!strcmp(name, "umma_desc_mode")) bvg::umma_desc_mode = value;
+  else if (!strcmp(name, "umma_max_ctas")) bvg::umma_max_ctas = value;
+  else {
+    bvg::set_error("unknown tuning knob '%s'", name);
+    return BVG_EINVAL;
+  }
+  return BVG_OK;
+}
+
+int bvg_amp_fwd(const bvg_amp_desc* d, void* stream) { return bvg::amp_forward(d, (cudaStream_t)stream); }
+int bvg_conv_fwd(const bvg_conv_desc* d, void* stream) { return bvg::conv_forward(d, (cudaStream_t)stream); }
+int bvg_post_fwd(const bvg_post_desc* d, void* stream) { return bvg::post_forward(d, (cudaStream_t)stream); }
+int bvg_pack_mel(const bvg_pack_desc* d, void* stream) { return bvg::pack_mel(d, (cudaStream_t)stream); }
+int bvg_convert(const bvg_tensor* src, const bvg_tensor* dst, size_t n, void* stream) {
+  return bvg::convert(src, dst, n, (cudaStream_t)stream);
+}
+
+int bvg_conv_geometry(const bvg_conv_geom* g, bvg_conv_weights* w) { return bvg::conv_geometry(g, w); }
+
+int bvg_conv_pack_bytes(const bvg_conv_geom* g, size_t* weight_plane_bytes, size_t* bias_bytes) {
+  bvg_conv_weights w;
+  memset(&w, 0, sizeof(w));
+  int rc = bvg::conv_geometry(g, &w);
+  if (rc != BVG_OK) return rc;
+  const size_t elems = bvg::conv_plane_elems(&w);
+  if (weight_plane_bytes) *weight_plane_bytes = elems * (w.backend == BVG_SIMT ? sizeof(float) : 2);
+  if (bias_bytes) *bias_bytes = (size_t)w.n_tiles * w.n_tile * sizeof(float);
+  return BVG_OK;
+}
+
+int bvg_pack_conv_weights(const bvg_conv_geom* g, const float* d_v, const float* d_g, const float* d_bias, bvg_conv_weights* w,
+                          float* d_bias_out, float* d_scratch, void* stream) {
+  return bvg::pack_conv_weights(g, d_v, d_g, d_bias, w, d_bias_out, d_scratch, (cudaStream_t)stream);
+}
+
+int bvg_pack_post_weights(const float* d_v, const float* d_g, int32_t cin, int32_t ksize, float* d_w_out, float* d_scratch, void* stream) {
+  return bvg::pack_post_weights(d_v, d_g, cin, ksize, d_w_out, d_scratch, (cudaStream_t)stream);
+}
+
+// ---- programs ---------------------------------------------------------------------------------
+int bvg_program_create(const bvg_op* ops, int32_t n_ops, bvg_program** out) {
+  if (!ops || n_ops < 0 || !out) {
+    bvg::set_error("program_create: bad argument");
+    return BVG_EINVAL;
+  }
+  bvg_program* p = new (std::nothrow) bvg_program();
+  if (!p) {
+    bvg::set_error("program_create: out of host memory");
+    return BVG_ENOMEM;
+  }
+  p->ops.assign(ops, ops + n_ops);
+  p->umma.assign(n_ops, nullptr);
+  for (int i = 0; i < n_ops; ++i) {
+    bvg_op& op = p->ops[i];
+    if (op.kind == BVG_OP_CONV) {
+      if (!op.u.conv.w) {
+        bvg::set_error("program_create: op %d has no weights", i);
+        delete p;
+        return BVG_EINVAL;
+      }
+      bvg_conv_weights* w = new bvg_conv_weights(*op.u.conv.w);
+      p->owned_weights.push_back(w);
+      op.u.conv.w = w;
+      if (w->backend == BVG_UMMA) {
+        void* rec = ::operator new(bvg::umma_launch_size());
+        p->umma[i] = rec;
+        int rc = bvg::conv_umma_prepare(&op.u.conv, reinterpret_cast<bvg::UmmaLaunch*>(rec));
+        if (rc != BVG_OK) {
+          delete p;
+          return rc;
+        }
+      }
+    } else if (op.kind != BVG_OP_PACK && op.kind != BVG_OP_AMP && op.kind != BVG_OP_POST) {
+      bvg::set_error("program_create: op %d has unknown kind %d", i, op.kind);
+      delete p;
+      return BVG_EINVAL;
+    }
+  }
+  p->launches = n_ops;
+  *out = p;
+  return BVG_OK;
+}
+
+static int run_one(bvg_program* p, size_t i, cudaStream_t st) {
+  const bvg_op& op = p->ops[i];
+  switch (op.kind) {
+    case BVG_OP_PACK: return bvg::pack_mel(&op.u.pack, st);
+    case BVG_OP_AMP: return bvg::amp_forward(&op.u.amp, st);
+    case BVG_OP_CONV:
+      return p->umma[i] ? bvg::conv_umma_launch(reinterpret_cast<const bvg::UmmaLaunch*>(p->umma[i]), st) : bvg::conv_forward(&op.u.conv, st);
+    case BVG_OP_POST: return bvg::post_forward(&op.u.post, st);
+    default: return BVG_EINVAL;
+  }
+}
+
+int bvg_program_run(bvg_program* p, void* stream) {
+  if (!p) {
+    bvg::set_error("program_run: null program");
+    return BVG_EINVAL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  for (size_t i = 0; i < p->ops.size(); ++i) {
+    int rc = run_one(p, i, st);
+    if (rc != BVG_OK) return rc;
+  }
+  return BVG_OK;
+}
+
+int bvg_program_run_timed(bvg_program* p, void* stream, float* ms_by_kind, int32_t* n_by_kind) {
+  if (!p || !ms_by_kind || !n_by_kind) {
+    bvg::set_error("program_run_timed: bad argument");
+    return BVG_EINVAL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = p->ops.size();
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) BVG_CHECK_CUDA(cudaEventCreate(&e));
+  int rc = BVG_OK;
+  for (size_t i = 0; i < n && rc == BVG_OK; ++i) {
+    cudaEventRecord(ev[i], st);
+    rc = run_one(p, i, st);
+  }
+  cudaEventRecord(ev[n], st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  for (int k = 0; k < 4; ++k) {
+    ms_by_kind[k] = 0.f;
+    n_by_kind[k] = 0;
+  }
+  if (rc == BVG_OK && e == cudaSuccess) {
+    for (size_t i = 0; i < n; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      const int k = p->ops[i].kind;
+      if (k >= 0 && k < 4) {
+        ms_by_kind[k] += ms;
+        n_by_kind[k] += 1;
+      }
+    }
+  }
+  for (auto& x : ev) cudaEventDestroy(x);
+  if (rc != BVG_OK) return rc;
+  if (e != cudaSuccess) return bvg::cuda_fail(e, "cudaStreamSynchronize (program_run_timed)");
+  return BVG_OK;
+}
+
+int bvg_program_num_launches(const bvg_program* p) { return p ? p->launches : 0; }
+void bvg_program_destroy(bvg_program* p) { delete p; }
+
+}  // extern "C"

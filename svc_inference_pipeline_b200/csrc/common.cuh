@@ -1,0 +1,61 @@
+// Shared helpers for libbvg_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/bvg_b200.h"
+
+namespace bvg {
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define BVG_CHECK_CUDA(expr)                                   \
+  do {                                                         \
+    cudaError_t _e = (expr);                                   \
+    if (_e != cudaSuccess) return ::bvg::cuda_fail(_e, #expr); \
+  } while (0)
+
+#define BVG_REQUIRE(cond, ...)        \
+  do {                                \
+    if (!(cond)) {                    \
+      ::bvg::set_error(__VA_ARGS__);  \
+      return BVG_EINVAL;              \
+    }                                 \
+  } while (0)
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+// ---- device-side element helpers ---------------------------------------------------------------
+__device__ __forceinline__ float bf16_bits_to_float(uint32_t hi16) { return __uint_as_float(hi16 << 16); }
+
+// round-to-nearest-even fp32 -> bf16, returned as the high 16 bits
+__device__ __forceinline__ uint32_t float_to_bf16_bits(float f) {
+  return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(f));
+}
+
+// pack two floats into one 32-bit word of two bf16 (lo half = first)
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ void unpack_bf16x2(uint32_t w, float& a, float& b) {
+  a = __uint_as_float(w << 16);
+  b = __uint_as_float(w & 0xffff0000u);
+}
+
+// hi = bf16(x), lo = bf16(x - hi): the two planes of a SPLIT tensor
+__device__ __forceinline__ void split_bf16(float x, float& hi, float& lo) {
+  hi = __bfloat162float(__float2bfloat16_rn(x));
+  lo = x - hi;  // exact in fp32; rounded to bf16 when packed
+}
+
+}  // namespace bvg

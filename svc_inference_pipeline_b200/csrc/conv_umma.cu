@@ -1,0 +1,518 @@
+// K-C / K-T: dense convolutions as a tap GEMM on the 5th-gen tensor cores (sm_100a).
+//
+// Replaces the weight-normed Conv1d layers of the AMP blocks and conv_pre, and the
+// ConvTranspose1d upsamplers (reference modules/bigvgan.py:319-386/:428-431, :529-537/:602,
+// :547-561/:607) in the formulation of include/bvg_b200.h:
+//     D[t, n] = sum_{tap} sum_{ci} X[t + shift(tap), ci] * W[n][tap][ci]
+// GEMM view per CTA tile: M = 128 time rows (TMEM lanes), N = n_tile output channels (TMEM
+// columns, fp32), K = taps x Cin streamed in 64-channel slices.
+//
+//  * operands are bf16, staged in shared memory by TMA (cp.async.bulk.tensor, 128B swizzle):
+//      A: one [rows x 64ch] box of the channels-last activation per Cin slice.  In HALO mode the
+//         box carries 128 + (max shift - min shift) rows and every tap reads it through a UMMA
+//         descriptor whose start address is advanced by (shift - min shift) rows, so a dilated
+//         k=11 layer loads each activation row once instead of 11 times.  Rows outside [0, L)
+//         are zero-filled by TMA (a 3-D map [B][L][C] keeps batch items apart) = Conv1d padding.
+//      B: one [n_tile x 64ch] box of the packed weights per (tap, Cin slice).
+//  * tcgen05.mma (cta_group::1, kind::f16, M=128, N=n_tile, K=16) issued by one thread,
+//    accumulating in TMEM; two accumulator stages so the epilogue of tile i overlaps tile i+1;
+//  * SPLIT operands (fp32-parity path): A and W come as (hi, lo) bf16 planes and each K slice
+//    issues hi*hi + lo*hi + hi*lo (3 MMAs, fp32 accumulate): 16 mantissa bits per operand;
+//  * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+//    warps 4-7 = epilogue (tcgen05.ld 32 lanes x 32 columns -> bias/residual/accumulate/divide
+//    -> F32 | BF16 | SPLIT stores).  Persistent: grid = min(#tiles, #SMs), static round-robin.
+//
+// Every mbarrier wait is bounded: a pipeline bug traps (launch failure) instead of hanging the GPU.
+#include <cuda.h>
+
+#include <cstring>
+
+#include "common.cuh"
+#include "epilogue.cuh"
+
+namespace bvg {
+
+constexpr int UM_BM = 128;          // rows per tile (TMEM lanes)
+constexpr int UM_KB = 64;           // channels per K slice (one 128-byte swizzle row of bf16)
+constexpr int UM_THREADS = 256;
+constexpr int UM_A_STAGES = 2;
+constexpr int UM_MAX_B_STAGES = 8;
+constexpr int UM_SMEM_LIMIT = 227 * 1024;
+
+struct UmmaParams {
+  CUtensorMap tm_x[2];  // activation planes (hi, lo)
+  CUtensorMap tm_w[2];  // weight planes (hi, lo)
+  EpiParams epi;
+  int planes;           // 1 (BF16) or 2 (SPLIT)
+  int B, L, N;
+  int n_tile, n_tiles, tap_stride;
+  int n_cb;             // Cin slices
+  int cin;              // true input channels (K steps of the last slice)
+  int m_tiles_per_item;
+  long long total_tiles;
+  int a_rows;           // rows per A box
+  int halo;             // 1: one A box per Cin slice shared by all taps; 0: one box per tap
+  int desc_mode;        // 0: base_offset = 0; 1: base_offset = (addr >> 7) & 7  (HALO row phase)
+  int b_stages;
+  int a_stage_bytes;    // all planes
+  int a_plane_bytes;
+  int b_stage_bytes;
+  int vec_ok;
+  int n_taps[BVG_MAX_NTILES];
+  int min_shift[BVG_MAX_NTILES];
+  int shift[BVG_MAX_NTILES][BVG_MAX_TAPS];
+  int* err_flag;        // optional device word set before a watchdog trap
+};
+
+namespace ptx {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// bounded wait: ~2 s at 2 GHz, then flag + trap
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err_flag, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {
+      if (err_flag) atomicExch(err_flag, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 x bf16 -> fp32, cta_group::1
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(addr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+}  // namespace ptx
+
+// UMMA shared-memory matrix descriptor, K-major operand, 128-byte swizzle:
+//   [0,14) start address >> 4   [16,30) leading byte offset >> 4 (unused for swizzled K-major)
+//   [32,46) stride byte offset >> 4 = 1024 B between 8-row groups   [46,48) version = 1
+//   [49,52) base offset   [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, int desc_mode) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  if (desc_mode == 1) d |= (uint64_t)((addr >> 7) & 7u) << 49;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// instruction descriptor: D=F32, A=B=BF16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_constant__ UmmaParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve-up: [A stages][B stages][barriers][tmem ptr]; base rounded up to 1024 B (swizzle atom)
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = a_base + UM_A_STAGES * p.a_stage_bytes;
+  const uint32_t bar_base = b_base + p.b_stages * p.b_stage_bytes;
+  // barrier words (8 B each)
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (UM_A_STAGES + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * UM_A_STAGES + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * UM_A_STAGES + UM_MAX_B_STAGES + s); };
+  auto t_full = [&](int s) { return bar_base + 8u * (2 * UM_A_STAGES + 2 * UM_MAX_B_STAGES + s); };
+  auto t_empty = [&](int s) { return bar_base + 8u * (2 * UM_A_STAGES + 2 * UM_MAX_B_STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * UM_A_STAGES + 2 * UM_MAX_B_STAGES + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.tm_x[0]);
+    ptx::prefetch_tmap(&p.tm_w[0]);
+    if (p.planes == 2) {
+      ptx::prefetch_tmap(&p.tm_x[1]);
+      ptx::prefetch_tmap(&p.tm_w[1]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < UM_A_STAGES; ++s) {
+      ptx::mbar_init(a_full(s), 1);
+      ptx::mbar_init(a_empty(s), 1);
+    }
+    for (int s = 0; s < p.b_stages; ++s) {
+      ptx::mbar_init(b_full(s), 1);
+      ptx::mbar_init(b_empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(t_full(s), 1);
+      ptx::mbar_init(t_empty(s), 4);  // one arrive per epilogue warp
+    }
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int planes = p.planes;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int sa = 0, pa = 0, sb = 0, pb = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = (int)(tile % p.n_tiles);
+        const long long mt = tile / p.n_tiles;
+        const int b = (int)(mt / p.m_tiles_per_item);
+        const int t0 = (int)(mt % p.m_tiles_per_item) * UM_BM;
+        const int ntaps = p.n_taps[nt];
+        for (int cb = 0; cb < p.n_cb; ++cb) {
+          for (int slot = 0; slot < ntaps; ++slot) {
+            if (!p.halo || slot == 0) {
+              const int row0 = t0 + (p.halo ? p.min_shift[nt] : p.shift[nt][slot]);
+              ptx::mbar_wait(a_empty(sa), pa ^ 1, p.err_flag, 1);
+              ptx::mbar_expect_tx(a_full(sa), (uint32_t)p.a_stage_bytes);
+              for (int pl = 0; pl < planes; ++pl)
+                ptx::tma_load_3d(a_base + sa * p.a_stage_bytes + pl * p.a_plane_bytes, &p.tm_x[pl], a_full(sa), cb * UM_KB, row0, b);
+              if (++sa == UM_A_STAGES) { sa = 0; pa ^= 1; }
+            }
+            for (int wp = 0; wp < planes; ++wp) {
+              ptx::mbar_wait(b_empty(sb), pb ^ 1, p.err_flag, 2);
+              ptx::mbar_expect_tx(b_full(sb), (uint32_t)p.b_stage_bytes);
+              ptx::tma_load_2d(b_base + sb * p.b_stage_bytes, &p.tm_w[wp], b_full(sb), cb * UM_KB,
+                               (nt * p.tap_stride + slot) * p.n_tile);
+              if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(p.n_tile);
+      int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, ap = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = (int)(tile % p.n_tiles);
+        const int ntaps = p.n_taps[nt];
+        ptx::mbar_wait(t_empty(as), ap ^ 1, p.err_flag, 3);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * 256);
+        uint32_t accumulate = 0;
+        for (int cb = 0; cb < p.n_cb; ++cb) {
+          const int valid = min(UM_KB, p.cin - cb * UM_KB);
+          const int ksteps = (valid + 15) >> 4;
+          uint32_t a_stage = 0;
+          for (int slot = 0; slot < ntaps; ++slot) {
+            if (!p.halo || slot == 0) {
+              ptx::mbar_wait(a_full(sa), pa, p.err_flag, 4);
+              a_stage = a_base + sa * p.a_stage_bytes;
+            }
+            const int row_off = p.halo ? (p.shift[nt][slot] - p.min_shift[nt]) : 0;
+            const uint32_t a_hi = a_stage + (uint32_t)row_off * 128u;
+            const uint32_t a_lo = a_hi + (uint32_t)p.a_plane_bytes;
+            for (int wp = 0; wp < planes; ++wp) {
+              ptx::mbar_wait(b_full(sb), pb, p.err_flag, 5);
+              ptx::tc_fence_after();
+              const uint32_t b_addr = b_base + sb * p.b_stage_bytes;
+              for (int k = 0; k < ksteps; ++k) {
+                const uint64_t bd = make_smem_desc(b_addr + k * 32, 0);
+                ptx::umma_f16(tmem_d, make_smem_desc(a_hi + k * 32, p.desc_mode), bd, idesc, accumulate);
+                accumulate = 1;
+                if (planes == 2 && wp == 0) ptx::umma_f16(tmem_d, make_smem_desc(a_lo + k * 32, p.desc_mode), bd, idesc, 1);
+              }
+              ptx::umma_commit(b_empty(sb));  // frees this weight stage when its MMAs retire
+              if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+            }
+            if (!p.halo || slot == ntaps - 1) {
+              ptx::umma_commit(a_empty(sa));
+              if (++sa == UM_A_STAGES) { sa = 0; pa ^= 1; }
+            }
+          }
+        }
+        ptx::umma_commit(t_full(as));  // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; ap ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ====================================
+    const int q = warp - 4;  // TMEM lane quarter == warp id % 4
+    int as = 0, ap = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = (int)(tile % p.n_tiles);
+      const long long mt = tile / p.n_tiles;
+      const int b = (int)(mt / p.m_tiles_per_item);
+      const int t = (int)(mt % p.m_tiles_per_item) * UM_BM + q * 32 + lane;
+      const bool row_ok = t < p.L;
+      const long long row = (long long)b * p.L + t;
+      ptx::mbar_wait(t_full(as), ap, p.err_flag, 6);
+      ptx::tc_fence_after();
+      const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
+      for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld32(tmem_row + (uint32_t)c0, r);
+        ptx::tmem_ld_wait();
+        if (row_ok) {
+          const int nbase = nt * p.n_tile + c0;
+          if (p.vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (c0 + j < p.n_tile && nbase + j < p.N) {
+                float v[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])};
+                epilogue4(p.epi, row, nbase + j, v);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < p.n_tile && nbase + j < p.N) epilogue1(p.epi, row, nbase + j, __uint_as_float(r[j]));
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(t_empty(as));
+      if (++as == 2) { as = 0; ap ^= 1; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+static int encode_bf16_map(CUtensorMap* map, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                           const cuuint32_t* box, const char* what) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return BVG_ECUDA;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d (base %p, rank %d, dims %llu/%llu/%llu, box %u/%u/%u)", what, (int)r, base, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], rank > 2 ? (unsigned long long)dims[2] : 0ull, box[0], box[1],
+              rank > 2 ? box[2] : 0u);
+    return BVG_ECUDA;
+  }
+  return BVG_OK;
+}
+
+int umma_a_mode = 1;     // tuning/test hook: 1 = HALO boxes, 0 = one box per tap
+int umma_desc_mode = 0;  // tuning/test hook: base_offset policy for row-shifted descriptors
+int umma_max_ctas = 0;   // tuning/test hook: cap the persistent grid
+
+struct UmmaLaunch {
+  UmmaParams p;
+  int grid;
+  size_t smem;
+};
+
+int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out) {
+  const bvg_conv_weights* w = d->w;
+  BVG_REQUIRE(w->backend == BVG_UMMA, "conv_umma: weights were packed for another backend");
+  BVG_REQUIRE(d->x.dtype == BVG_BF16 || d->x.dtype == BVG_SPLIT, "conv_umma: input must be BF16 or SPLIT");
+  const int planes = d->x.dtype == BVG_SPLIT ? 2 : 1;
+  BVG_REQUIRE(planes == 1 || (w->split && w->d_w_lo && d->x.d_lo), "conv_umma: SPLIT input needs split-packed weights and a lo plane");
+  BVG_REQUIRE(d->x.d_ptr && w->d_w, "conv_umma: null pointer");
+  BVG_REQUIRE(d->B > 0 && d->L > 0, "conv_umma: bad shape");
+  BVG_REQUIRE(w->n_tile % 16 == 0 && w->n_tile >= 16 && w->n_tile <= 256, "conv_umma: bad n_tile %d", w->n_tile);
+  BVG_REQUIRE(w->n_tiles <= BVG_MAX_NTILES, "conv_umma: too many N tiles");
+  BVG_REQUIRE(w->x_pitch % 8 == 0, "conv_umma: channel pitch %d must be a multiple of 8 (16-byte TMA strides)", w->x_pitch);
+  BVG_REQUIRE(((uintptr_t)d->x.d_ptr & 15) == 0 && ((uintptr_t)w->d_w & 15) == 0, "conv_umma: operands must be 16-byte aligned");
+
+  UmmaParams& p = out->p;
+  memset(&p, 0, sizeof(p));
+  int rc = fill_epilogue(d, p.epi);
+  if (rc != BVG_OK) return rc;
+  p.planes = planes;
+  p.B = d->B;
+  p.L = d->L;
+  p.N = w->n_total;
+  p.n_tile = w->n_tile;
+  p.n_tiles = w->n_tiles;
+  p.tap_stride = w->tap_stride;
+  p.n_cb = w->cin_pad / UM_KB;
+  p.cin = w->cin;
+  p.m_tiles_per_item = ceil_div(d->L, UM_BM);
+  p.total_tiles = (long long)d->B * p.m_tiles_per_item * w->n_tiles;
+  p.vec_ok = (w->n_total % 4 == 0) ? 1 : 0;
+  p.desc_mode = umma_desc_mode;
+  int max_span = 0;
+  for (int t = 0; t < w->n_tiles; ++t) {
+    BVG_REQUIRE(w->n_taps[t] > 0 && w->n_taps[t] <= BVG_MAX_TAPS, "conv_umma: bad tap count");
+    int lo = w->shift[t][0], hi = w->shift[t][0];
+    for (int k = 0; k < w->n_taps[t]; ++k) {
+      p.shift[t][k] = w->shift[t][k];
+      lo = w->shift[t][k] < lo ? w->shift[t][k] : lo;
+      hi = w->shift[t][k] > hi ? w->shift[t][k] : hi;
+    }
+    p.n_taps[t] = w->n_taps[t];
+    p.min_shift[t] = lo;
+    if (hi - lo > max_span) max_span = hi - lo;
+  }
+  p.halo = (umma_a_mode != 0 && UM_BM + max_span <= 256) ? 1 : 0;
+  p.a_rows = p.halo ? ((UM_BM + max_span + 7) / 8) * 8 : UM_BM;
+  p.a_plane_bytes = p.a_rows * 128;
+  p.a_stage_bytes = p.a_plane_bytes * planes;
+  p.b_stage_bytes = w->n_tile * 128;
+  const int bar_bytes = 8 * (2 * UM_A_STAGES + 2 * UM_MAX_B_STAGES + 4) + 16;
+  const int avail = UM_SMEM_LIMIT - 1024 /*alignment slack*/ - bar_bytes - UM_A_STAGES * p.a_stage_bytes;
+  int bs = avail / p.b_stage_bytes;
+  if (bs > UM_MAX_B_STAGES) bs = UM_MAX_B_STAGES;
+  BVG_REQUIRE(bs >= 2, "conv_umma: tile does not fit in shared memory (a_rows %d, n_tile %d)", p.a_rows, w->n_tile);
+  p.b_stages = bs;
+  size_t smem = 1024 + (size_t)UM_A_STAGES * p.a_stage_bytes + (size_t)bs * p.b_stage_bytes + bar_bytes;
+  // keep one CTA per SM (each allocates all 512 TMEM columns): ask for more than half the SM's smem
+  if (smem < 120 * 1024) smem = 120 * 1024;
+  out->smem = smem;
+
+  // tensor maps
+  for (int pl = 0; pl < planes; ++pl) {
+    void* xb = pl == 0 ? d->x.d_ptr : d->x.d_lo;
+    cuuint64_t dims[3] = {(cuuint64_t)w->x_pitch, (cuuint64_t)d->L, (cuuint64_t)d->B};
+    cuuint64_t strides[2] = {(cuuint64_t)w->x_pitch * 2, (cuuint64_t)w->x_pitch * 2 * (cuuint64_t)d->L};
+    cuuint32_t box[3] = {(cuuint32_t)UM_KB, (cuuint32_t)p.a_rows, 1};
+    rc = encode_bf16_map(&p.tm_x[pl], xb, 3, dims, strides, box, "activation");
+    if (rc != BVG_OK) return rc;
+    void* wb = pl == 0 ? w->d_w : w->d_w_lo;
+    cuuint64_t wdims[2] = {(cuuint64_t)w->cin_pad, (cuuint64_t)w->n_tiles * w->tap_stride * w->n_tile};
+    cuuint64_t wstrides[1] = {(cuuint64_t)w->cin_pad * 2};
+    cuuint32_t wbox[2] = {(cuuint32_t)UM_KB, (cuuint32_t)w->n_tile};
+    rc = encode_bf16_map(&p.tm_w[pl], wb, 2, wdims, wstrides, wbox, "weights");
+    if (rc != BVG_OK) return rc;
+  }
+
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long grid = p.total_tiles < sms ? p.total_tiles : sms;
+  if (umma_max_ctas > 0 && grid > umma_max_ctas) grid = umma_max_ctas;
+  out->grid = (int)grid;
+  return BVG_OK;
+}
+
+int conv_umma_launch(const UmmaLaunch* l, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    BVG_CHECK_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_LIMIT));
+    attr_set = true;
+  }
+  if (l->grid <= 0) return BVG_OK;
+  conv_umma_kernel<<<l->grid, UM_THREADS, l->smem, st>>>(l->p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "conv_umma_kernel launch");
+  return BVG_OK;
+}
+
+size_t umma_launch_size() { return sizeof(UmmaLaunch); }
+
+int conv_umma_forward(const bvg_conv_desc* d, cudaStream_t st) {
+  UmmaLaunch l;
+  int rc = conv_umma_prepare(d, &l);
+  if (rc != BVG_OK) return rc;
+  return conv_umma_launch(&l, st);
+}
+
+}  // namespace bvg

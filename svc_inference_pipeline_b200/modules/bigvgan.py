@@ -1,0 +1,527 @@
+"""B200-native BigVGAN generator with the reference's call surface.
+
+Drop-in for the generator half of the reference's ``modules/bigvgan.py`` (lines 1-632):
+
+* ``Generator(cfg.vocoder)`` reads the same hyper-parameters (``modules/bigvgan.py:521-598``),
+* ``state_dict()`` / ``load_state_dict()`` use the same 784 keys and shapes (``weight_g`` /
+  ``weight_v`` / ``bias``, ``act.alpha`` / ``act.beta``, the persistent 12-tap filter buffers), so
+  checkpoints saved as ``{"generator_state_dict": ...}`` load unchanged,
+* ``forward(mel[B, input_dim, T]) -> wave[B, 1, T * prod(upsample_rates)]`` (``:600-622``),
+* ``remove_weight_norm()`` (``:624-632``), ``.parameters()``, ``.eval()``.
+
+Nothing is computed with PyTorch operators.  The module owns tensors (parameters, packed weights,
+activations workspace) and drives ``libbvg_b200.so`` through its C ABI: weight-norm is folded once
+at load, and one forward is a pre-built *program* of ~235 kernel launches (fused anti-aliased
+activations + tcgen05 tap-GEMM convolutions) issued by a single C call.  There is no CPU path.
+
+Numeric modes (``precision=``):
+
+``"fp32"``       conv operands are (hi, lo) bf16 pairs, 3 tensor-core products per K slice with fp32
+                 accumulation; activations stay fp32.  Parity target: 1e-4 max-abs vs the reference.
+``"bf16"``       bf16 operands and bf16 activation storage, fp32 accumulation / fp32 AMP math.
+``"fp32_simt"``  every conv on CUDA cores in true fp32 (FFMA): slow exact anchor.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from collections import OrderedDict
+
+import torch
+from torch import nn
+
+from .. import _lib as L
+from ..utils import synth
+
+__all__ = ["Generator", "get_padding"]
+
+
+def get_padding(kernel_size: int, dilation: int = 1) -> int:
+    return int((kernel_size * dilation - dilation) / 2)
+
+
+# ----------------------------------------------------------------------------------------------
+# parameter holders: only there to give parameters/buffers the reference's names
+# ----------------------------------------------------------------------------------------------
+class _WNConv(nn.Module):
+    """Weight-normed Conv1d / ConvTranspose1d parameters (``bias``, ``weight_g``, ``weight_v``)."""
+
+    def __init__(self, cin, cout, ksize, *, dilation=1, stride=1, padding=0, transposed=False):
+        super().__init__()
+        self.cin, self.cout, self.ksize = cin, cout, ksize
+        self.dilation, self.stride, self.padding, self.transposed = dilation, stride, padding, transposed
+        shape = (cin, cout, ksize) if transposed else (cout, cin, ksize)
+        v = torch.empty(shape)
+        nn.init.kaiming_uniform_(v, a=math.sqrt(5))
+        bound = 1.0 / math.sqrt(shape[1] * ksize)
+        self.bias = nn.Parameter(torch.empty(cout).uniform_(-bound, bound))
+        self.weight_g = nn.Parameter(v.flatten(1).norm(dim=1).reshape(-1, 1, 1))
+        self.weight_v = nn.Parameter(v)
+
+    def folded(self) -> bool:
+        return self.weight_g is None
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        # accept an already-folded ".weight" (a checkpoint saved after remove_weight_norm())
+        if prefix + "weight" in state_dict and prefix + "weight_v" not in state_dict:
+            w = state_dict.pop(prefix + "weight")
+            state_dict[prefix + "weight_v"] = w
+            dim0 = w.shape[0]
+            state_dict[prefix + "weight_g"] = w.flatten(1).norm(dim=1).reshape(dim0, 1, 1)
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+
+class _Snake(nn.Module):
+    def __init__(self, channels, beta: bool, logscale: bool):
+        super().__init__()
+        init = torch.zeros if logscale else torch.ones
+        self.alpha = nn.Parameter(init(channels))
+        if beta:
+            self.beta = nn.Parameter(init(channels))
+        self.alpha_logscale = logscale
+        self.no_div_by_zero = 0.000000001
+
+
+class _Filter(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.register_buffer("filter", torch.from_numpy(synth.aa_filter_taps()).reshape(1, 1, 12).clone())
+
+
+class _Down(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.lowpass = _Filter()
+
+
+class _Activation1d(nn.Module):
+    def __init__(self, channels, activation: str, logscale: bool):
+        super().__init__()
+        self.act = _Snake(channels, beta=(activation == "snakebeta"), logscale=logscale)
+        self.upsample = _Filter()
+        self.downsample = _Down()
+
+
+def _check_activation(name):
+    if name not in ("snake", "snakebeta"):
+        raise NotImplementedError("activation incorrectly specified. check the config file and look for 'activation'.")
+
+
+class _AMPBlock1(nn.Module):
+    def __init__(self, cfg, channels, kernel_size, dilation, activation):
+        super().__init__()
+        _check_activation(activation)
+        self.kernel_size, self.dilation = kernel_size, tuple(dilation)
+        self.convs1 = nn.ModuleList(
+            [_WNConv(channels, channels, kernel_size, dilation=d, padding=get_padding(kernel_size, d)) for d in dilation]
+        )
+        self.convs2 = nn.ModuleList(
+            [_WNConv(channels, channels, kernel_size, dilation=1, padding=get_padding(kernel_size, 1)) for _ in dilation]
+        )
+        self.num_layers = len(self.convs1) + len(self.convs2)
+        self.activations = nn.ModuleList([_Activation1d(channels, activation, cfg.snake_logscale) for _ in range(self.num_layers)])
+
+
+class _AMPBlock2(nn.Module):
+    def __init__(self, cfg, channels, kernel_size, dilation, activation):
+        super().__init__()
+        _check_activation(activation)
+        self.kernel_size, self.dilation = kernel_size, tuple(dilation)
+        self.convs = nn.ModuleList(
+            [_WNConv(channels, channels, kernel_size, dilation=d, padding=get_padding(kernel_size, d)) for d in dilation]
+        )
+        self.num_layers = len(self.convs)
+        self.activations = nn.ModuleList([_Activation1d(channels, activation, cfg.snake_logscale) for _ in range(self.num_layers)])
+
+
+# ----------------------------------------------------------------------------------------------
+# device-side plumbing
+# ----------------------------------------------------------------------------------------------
+class _Buf:
+    """A channels-last activation buffer in one of the library's element formats."""
+
+    _TORCH = {L.F32: torch.float32, L.BF16: torch.bfloat16, L.SPLIT: torch.bfloat16}
+
+    def __init__(self, dtype, numel, device):
+        self.dtype = dtype
+        self.hi = torch.empty(numel, dtype=self._TORCH[dtype], device=device)
+        self.lo = torch.empty(numel, dtype=torch.bfloat16, device=device) if dtype == L.SPLIT else None
+
+    def tensor(self) -> L.Tensor:
+        return L.Tensor(self.hi.data_ptr(), self.lo.data_ptr() if self.lo is not None else None, self.dtype, 0)
+
+    def nbytes(self):
+        return self.hi.numel() * self.hi.element_size() + (self.lo.numel() * 2 if self.lo is not None else 0)
+
+
+_NULL = L.Tensor(None, None, L.F32, 0)
+
+
+class _PackedConv:
+    """Folded + packed weights of one conv layer, resident on the device."""
+
+    def __init__(self, conv: _WNConv, backend: int, split: bool, stream):
+        lib = L.lib()
+        dev = conv.weight_v.device
+        self.geom = L.ConvGeom(
+            int(conv.transposed), conv.cin, conv.cout, conv.ksize, conv.dilation, conv.stride, conv.padding, backend, int(split), 0
+        )
+        wb, bb = C.c_size_t(), C.c_size_t()
+        L.check(lib.bvg_conv_pack_bytes(C.byref(self.geom), C.byref(wb), C.byref(bb)), "conv_pack_bytes")
+        self.w_hi = torch.empty(wb.value, dtype=torch.uint8, device=dev)
+        self.w_lo = torch.empty(wb.value, dtype=torch.uint8, device=dev) if (split and backend == L.UMMA) else None
+        self.bias = torch.empty(bb.value // 4, dtype=torch.float32, device=dev)
+        scratch = torch.empty(max(conv.cin, conv.cout), dtype=torch.float32, device=dev)
+        self.desc = L.ConvWeights()
+        self.desc.d_w = self.w_hi.data_ptr()
+        self.desc.d_w_lo = self.w_lo.data_ptr() if self.w_lo is not None else None
+        v = conv.weight_v.detach().contiguous().float()
+        g = conv.weight_g.detach().contiguous().float() if conv.weight_g is not None else None
+        b = conv.bias.detach().contiguous().float()
+        L.check(
+            lib.bvg_pack_conv_weights(
+                C.byref(self.geom), v.data_ptr(), g.data_ptr() if g is not None else None, b.data_ptr(), C.byref(self.desc), self.bias.data_ptr(), scratch.data_ptr(), stream
+            ),
+            "pack_conv_weights",
+        )
+        self._keep = (v, g, b, scratch)
+        self.n_total = self.desc.n_total
+        self.x_pitch = self.desc.x_pitch
+
+    def nbytes(self):
+        return self.w_hi.numel() + (self.w_lo.numel() if self.w_lo is not None else 0) + self.bias.numel() * 4
+
+
+class _Program:
+    def __init__(self, ops, keep, mel_in, out, launches):
+        arr = (L.Op * len(ops))(*ops)
+        handle = C.c_void_p()
+        L.check(L.lib().bvg_program_create(arr, len(ops), C.byref(handle)), "program_create")
+        self.handle, self.keep, self.mel_in, self.out, self.launches = handle, keep, mel_in, out, launches
+        self.graph = None
+
+    def run(self, stream):
+        L.check(L.lib().bvg_program_run(self.handle, stream), "program_run")
+
+    def __del__(self):
+        try:
+            if self.handle:
+                L.lib().bvg_program_destroy(self.handle)
+        except Exception:
+            pass
+
+
+_MODES = {
+    #             backend, operand dtype, stream dtype, mid dtype, fast_sin
+    "fp32": (L.UMMA, L.SPLIT, L.F32, L.F32, 0),
+    "bf16": (L.UMMA, L.BF16, L.BF16, L.BF16, 1),
+    "fp32_simt": (L.SIMT, L.F32, L.F32, L.F32, 0),
+}
+
+
+class Generator(nn.Module):
+    """BigVGAN generator (reference ``modules/bigvgan.py:519-632``) running on libbvg_b200."""
+
+    def __init__(self, cfg, precision: str = "fp32"):
+        super().__init__()
+        self.cfg = cfg
+        _check_activation(cfg.activation)
+        if precision not in _MODES:
+            raise ValueError(f"precision must be one of {sorted(_MODES)}")
+        self.precision = precision
+        self.num_kernels = len(cfg.resblock_kernel_sizes)
+        self.num_upsamples = len(cfg.upsample_rates)
+        c0 = cfg.upsample_initial_channel
+        self.conv_pre = _WNConv(cfg.input_dim, c0, 7, padding=3)
+        block = _AMPBlock1 if cfg.resblock == "1" else _AMPBlock2
+        self.ups = nn.ModuleList()
+        for i, (u, k) in enumerate(zip(cfg.upsample_rates, cfg.upsample_kernel_sizes)):
+            self.ups.append(nn.ModuleList([_WNConv(c0 // 2**i, c0 // 2 ** (i + 1), k, stride=u, padding=(k - u) // 2, transposed=True)]))
+        self.resblocks = nn.ModuleList()
+        ch = c0
+        for i in range(len(self.ups)):
+            ch = c0 // 2 ** (i + 1)
+            for k, d in zip(cfg.resblock_kernel_sizes, cfg.resblock_dilation_sizes):
+                self.resblocks.append(block(cfg, ch, k, d, cfg.activation))
+        self.activation_post = _Activation1d(ch, cfg.activation, cfg.snake_logscale)
+        self.conv_post = _WNConv(ch, 1, 7, padding=3)
+        self.hop = int(math.prod(cfg.upsample_rates))
+        self._packed = None
+        self._programs: "OrderedDict[tuple, _Program]" = OrderedDict()
+        self.max_cached_programs = 4
+        self.use_cuda_graph = False
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
+
+    # -- nn.Module plumbing -------------------------------------------------------------------
+    def _invalidate(self):
+        self._packed = None
+        self._programs.clear()
+
+    def _apply(self, fn, *args, **kwargs):
+        self._invalidate()
+        return super()._apply(fn, *args, **kwargs)
+
+    def set_precision(self, precision: str):
+        if precision not in _MODES:
+            raise ValueError(f"precision must be one of {sorted(_MODES)}")
+        if precision != self.precision:
+            self.precision = precision
+            self._invalidate()
+        return self
+
+    def remove_weight_norm(self):
+        """Reference ``modules/bigvgan.py:624-632``.  Weight norm is folded at pack time anyway;
+        this makes the fold permanent in the parameters (``weight_v`` <- folded weight, ``weight_g``
+        <- its norm), which leaves every output unchanged."""
+        print("Removing weight norm...")
+        with torch.no_grad():
+            for m in self.modules():
+                if isinstance(m, _WNConv):
+                    v = m.weight_v
+                    w = v * (m.weight_g / v.flatten(1).norm(dim=1).reshape(-1, 1, 1))
+                    m.weight_v.copy_(w)
+                    m.weight_g.copy_(w.flatten(1).norm(dim=1).reshape(-1, 1, 1))
+        self._invalidate()
+
+    # -- load-time packing ----------------------------------------------------------------------
+    def _device(self):
+        return self.conv_pre.weight_v.device
+
+    def _require_cuda(self):
+        dev = self._device()
+        if dev.type != "cuda":
+            raise RuntimeError(
+                "svc_inference_pipeline_b200.Generator has no CPU path: move the model to a B200 "
+                "(cfg.device = 'cuda' in vocoder_model_loader, or model.cuda())"
+            )
+        L.check(L.lib().bvg_device_check(dev.index if dev.index is not None else torch.cuda.current_device()), "device_check")
+        return dev
+
+    def _act_params(self, a1d: _Activation1d):
+        act = a1d.act
+        alpha = act.alpha.detach().float()
+        beta = act.beta.detach().float() if hasattr(act, "beta") else alpha
+        if act.alpha_logscale:
+            alpha, beta = torch.exp(alpha), torch.exp(beta)
+        invb = 1.0 / (beta + act.no_div_by_zero)
+        up = a1d.upsample.filter.detach().float().reshape(-1).cpu().tolist()
+        down = a1d.downsample.lowpass.filter.detach().float().reshape(-1).cpu().tolist()
+        return alpha.contiguous(), invb.contiguous(), up, down
+
+    def _pack(self):
+        dev = self._require_cuda()
+        backend, op_dt, _, _, _ = _MODES[self.precision]
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        split = op_dt == L.SPLIT
+        packed = {"conv": {}, "act": {}}
+        with torch.cuda.device(dev):
+            for name, m in self.named_modules():
+                if isinstance(m, _WNConv) and name != "conv_post":
+                    be = backend
+                    if be == L.UMMA and not self._umma_ok(m):
+                        raise RuntimeError(
+                            f"layer {name} ({m.cin}->{m.cout}) cannot run on the tensor-core path "
+                            "(channel counts must be multiples of 8); use precision='fp32_simt'"
+                        )
+                    packed["conv"][name] = _PackedConv(m, be, split, stream)
+                elif isinstance(m, _Activation1d):
+                    packed["act"][name] = self._act_params(m)
+            cp = self.conv_post
+            wpost = torch.empty(cp.cin * cp.ksize, dtype=torch.float32, device=dev)
+            scratch = torch.empty(1, dtype=torch.float32, device=dev)
+            v = cp.weight_v.detach().contiguous().float()
+            g = cp.weight_g.detach().contiguous().float()
+            L.check(L.lib().bvg_pack_post_weights(v.data_ptr(), g.data_ptr(), cp.cin, cp.ksize, wpost.data_ptr(), scratch.data_ptr(), stream), "pack_post_weights")
+            packed["post_w"] = wpost
+            packed["post_bias"] = float(cp.bias.detach().float().cpu()[0])
+            torch.cuda.current_stream(dev).synchronize()
+        self._packed = packed
+
+    def _umma_ok(self, m: _WNConv) -> bool:
+        if m is self.conv_pre:
+            return m.cout % 8 == 0
+        return m.cin % 8 == 0 and (m.cout % 8 == 0)
+
+    def packed_weight_bytes(self) -> int:
+        if self._packed is None:
+            self._pack()
+        return sum(p.nbytes() for p in self._packed["conv"].values())
+
+    # -- program construction ---------------------------------------------------------------------
+    def _build_program(self, B: int, T: int) -> _Program:
+        if self._packed is None:
+            self._pack()
+        dev = self._device()
+        backend, op_dt, st_dt, mid_dt, fast_sin = _MODES[self.precision]
+        pk = self._packed
+        cfg = self.cfg
+        ops, keep = [], []
+
+        def conv_op(name, x, out, B_, L_, res=None, acc=None, div=1.0):
+            op = L.Op()
+            op.kind = L.OP_CONV
+            d = op.u.conv
+            d.x, d.out = x.tensor(), out.tensor()
+            d.res = res.tensor() if res is not None else _NULL
+            d.acc_in = acc.tensor() if acc is not None else _NULL
+            d.div, d.B, d.L = float(div), B_, L_
+            d.w = C.pointer(pk["conv"][name].desc)
+            ops.append(op)
+
+        def amp_op(name, x, y, B_, L_, C_):
+            a, invb, up, down = pk["act"][name]
+            op = L.Op()
+            op.kind = L.OP_AMP
+            d = op.u.amp
+            d.x, d.y = x.tensor(), y.tensor()
+            d.d_a, d.d_invb = a.data_ptr(), invb.data_ptr()
+            d.taps_up = (C.c_float * 12)(*up)
+            d.taps_down = (C.c_float * 12)(*down)
+            d.B, d.L, d.C, d.fast_sin = B_, L_, C_, fast_sin
+            ops.append(op)
+
+        # stage geometry
+        c0 = cfg.upsample_initial_channel
+        lens, chans = [], []
+        ln = T
+        for i, u in enumerate(cfg.upsample_rates):
+            ln *= u
+            lens.append(ln)
+            chans.append(c0 // 2 ** (i + 1))
+        max_elems = max(B * l * c for l, c in zip(lens, chans))
+
+        mel_in = torch.empty(B, cfg.input_dim, T, dtype=torch.float32, device=dev)
+        pre = pk["conv"]["conv_pre"]
+        melp = _Buf(op_dt, B * T * pre.x_pitch, dev)
+        h = _Buf(op_dt, max(B * T * c0, max_elems), dev)        # operand-format stage input (ping)
+        h2 = _Buf(op_dt, max_elems, dev)                         # (pong)
+        x_in = _Buf(st_dt, max_elems, dev)
+        xa = _Buf(st_dt, max_elems, dev)
+        xs = _Buf(st_dt, max_elems, dev)
+        t_op = _Buf(op_dt, max_elems, dev)
+        t_mid = _Buf(mid_dt, max_elems, dev)
+        y_post = _Buf(st_dt, B * lens[-1] * chans[-1], dev)
+        out = torch.empty(B, 1, lens[-1], dtype=torch.float32, device=dev)
+        keep += [mel_in, melp, h, h2, x_in, xa, xs, t_op, t_mid, y_post, out]
+
+        op = L.Op()
+        op.kind = L.OP_PACK
+        op.u.pack.d_mel = mel_in.data_ptr()
+        op.u.pack.out = melp.tensor()
+        op.u.pack.B, op.u.pack.C, op.u.pack.T, op.u.pack.c_pad = B, cfg.input_dim, T, pre.x_pitch
+        ops.append(op)
+        conv_op("conv_pre", melp, h, B, T)
+
+        cur, nxt = h, h2
+        l_in = T
+        nk = self.num_kernels
+        block1 = cfg.resblock == "1"
+        for i in range(self.num_upsamples):
+            ln, ch = lens[i], chans[i]
+            # transposed conv: GEMM over the *input* rows, output viewed as [B, l_in, u*ch]
+            conv_op(f"ups.{i}.0", cur, x_in, B, l_in)
+            last_stage = i == self.num_upsamples - 1
+            stage_out = y_post if last_stage else nxt
+            for j in range(nk):
+                rb = f"resblocks.{i * nk + j}"
+                nl = len(self.resblocks[i * nk + j].dilation)
+                xj = x_in
+                for l in range(nl):
+                    final = l == nl - 1
+                    if block1:
+                        amp_op(f"{rb}.activations.{2 * l}", xj, t_op, B, ln, ch)
+                        conv_op(f"{rb}.convs1.{l}", t_op, t_mid, B, ln)
+                        amp_op(f"{rb}.activations.{2 * l + 1}", t_mid, t_op, B, ln, ch)
+                        cname = f"{rb}.convs2.{l}"
+                    else:
+                        amp_op(f"{rb}.activations.{l}", xj, t_op, B, ln, ch)
+                        cname = f"{rb}.convs.{l}"
+                    if not final:
+                        conv_op(cname, t_op, xa, B, ln, res=xj)
+                        xj = xa
+                    elif j == 0 and nk > 1:
+                        conv_op(cname, t_op, xs, B, ln, res=xj)
+                    elif j < nk - 1:
+                        conv_op(cname, t_op, xs, B, ln, res=xj, acc=xs)
+                    else:
+                        # last resblock: (xs + this) / num_kernels, stored in the next consumer's format
+                        conv_op(cname, t_op, stage_out, B, ln, res=xj, acc=(xs if nk > 1 else None), div=float(nk))
+            cur, nxt = nxt, cur
+            l_in = ln
+
+        amp_op("activation_post", y_post, xa, B, lens[-1], chans[-1])
+        op = L.Op()
+        op.kind = L.OP_POST
+        d = op.u.post
+        d.x = xa.tensor()
+        d.d_w = pk["post_w"].data_ptr()
+        d.bias = pk["post_bias"]
+        d.d_out = out.data_ptr()
+        d.B, d.L, d.C, d.ksize = B, lens[-1], chans[-1], self.conv_post.ksize
+        ops.append(op)
+        return _Program(ops, keep, mel_in, out, len(ops))
+
+    def _program(self, B: int, T: int) -> _Program:
+        key = (B, T, self.precision)
+        prog = self._programs.get(key)
+        if prog is None:
+            with torch.cuda.device(self._device()):
+                prog = self._build_program(B, T)
+            self._programs[key] = prog
+            while len(self._programs) > self.max_cached_programs:
+                self._programs.popitem(last=False)
+        else:
+            self._programs.move_to_end(key)
+        return prog
+
+    def workspace_bytes(self, B: int, T: int) -> int:
+        return sum(k.nbytes() if isinstance(k, _Buf) else k.numel() * k.element_size() for k in self._program(B, T).keep)
+
+    def launches_per_forward(self, B: int, T: int) -> int:
+        return self._program(B, T).launches
+
+    def profile_classes(self, B: int, T: int, reps: int = 1) -> dict:
+        """Device time per kernel class for one forward of shape (B, T): CUDA events between
+        consecutive launches of the program (``bvg_program_run_timed``).  The mel staging buffer
+        keeps whatever the last forward left in it."""
+        dev = self._require_cuda()
+        prog = self._program(B, T)
+        ms = (C.c_float * 4)()
+        cnt = (C.c_int32 * 4)()
+        tot = [0.0] * 4
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            for _ in range(max(1, reps)):
+                L.check(L.lib().bvg_program_run_timed(prog.handle, stream, ms, cnt), "program_run_timed")
+                for k in range(4):
+                    tot[k] += ms[k] / max(1, reps)
+        return {
+            "conv_ms": tot[L.OP_CONV], "conv_n": cnt[L.OP_CONV], "amp_ms": tot[L.OP_AMP], "amp_n": cnt[L.OP_AMP],
+            "other_ms": tot[L.OP_PACK] + tot[L.OP_POST], "total_ms": sum(tot),
+        }
+
+    # -- forward ----------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        dev = self._require_cuda()
+        if x.dim() != 3 or x.shape[1] != self.cfg.input_dim:
+            raise ValueError(f"expected mel of shape [B, {self.cfg.input_dim}, T], got {tuple(x.shape)}")
+        B, _, T = x.shape
+        if B == 0 or T == 0:
+            return torch.empty(B, 1, T * self.hop, dtype=torch.float32, device=dev)
+        prog = self._program(B, T)
+        with torch.cuda.device(dev):
+            prog.mel_in.copy_(x, non_blocking=True)
+            stream = torch.cuda.current_stream(dev)
+            if self.use_cuda_graph:
+                if prog.graph is None:
+                    prog.run(stream.cuda_stream)  # warm-up outside capture (lazy function attributes)
+                    stream.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        prog.run(torch.cuda.current_stream(dev).cuda_stream)
+                    prog.graph = g
+                prog.graph.replay()
+            else:
+                prog.run(stream.cuda_stream)
+            return prog.out.clone()

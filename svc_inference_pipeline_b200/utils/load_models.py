@@ -1,0 +1,52 @@
+"""Checkpoint loading with the reference's call surface (reference ``utils/load_models.py:52-79``).
+
+``vocoder_model_loader(cfg)`` builds ``Generator(cfg.vocoder)``, reads
+``torch.load(cfg.vocoder_model_path)["generator_state_dict"]``, strips a ``module.`` prefix
+(``k.split("module.")[-1]``), keeps only tensors whose name *and* shape match, loads them, moves the
+model to CUDA iff ``cfg.device == "cuda"`` and puts it in eval mode.  The one deliberate
+difference: the reference drops mismatched tensors silently (they keep their random init);
+this loader does the same but *reports* them (``model.load_report``) and warns.
+"""
+from __future__ import annotations
+
+import warnings
+
+import torch
+
+from ..modules.bigvgan import Generator
+
+
+def filter_state_dict(pretrained: dict, target: dict):
+    """The reference's name+shape filter (``utils/load_models.py:63-70``) plus a report."""
+    kept, wrong_shape, unknown = {}, [], []
+    for k, v in pretrained.items():
+        name = k.split("module.")[-1]
+        if name not in target:
+            unknown.append(name)
+        elif tuple(v.shape) != tuple(target[name].shape):
+            wrong_shape.append((name, tuple(v.shape), tuple(target[name].shape)))
+        else:
+            kept[name] = v
+    missing = [k for k in target if k not in kept]
+    return kept, {"missing": missing, "wrong_shape": wrong_shape, "unknown": unknown}
+
+
+def vocoder_model_loader(cfg, precision: str = "fp32"):
+    print("Loading vocoder model from ", cfg.vocoder_model_path)
+    model = Generator(cfg.vocoder, precision=precision)
+    ckpt = torch.load(cfg.vocoder_model_path, map_location=torch.device(cfg.device))
+    pretrained = ckpt["generator_state_dict"]
+    generator_dict = model.state_dict()
+    kept, report = filter_state_dict(pretrained, generator_dict)
+    generator_dict.update(kept)
+    model.load_state_dict(generator_dict)
+    model.load_report = report
+    if report["missing"] or report["wrong_shape"] or report["unknown"]:
+        warnings.warn(
+            f"vocoder checkpoint: {len(report['missing'])} tensors keep their init values, "
+            f"{len(report['wrong_shape'])} had a mismatched shape, {len(report['unknown'])} were not recognised"
+        )
+    if cfg.device == "cuda":
+        model = model.cuda()
+    model = model.eval()
+    return model

@@ -1,0 +1,178 @@
+"""Whole-generator parity on the GPU against reference-generated golden vectors
+(tests/golden/*.npz) and the CPU oracle.  Needs a B200: run with ``-m gpu``."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bigvgan_oracle as O
+from util_cases import REPO, TINY_VARIANTS, V2, snr_db, tiny_cfg_sd
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def build(cfgd, sd, precision):
+    from svc_inference_pipeline_b200.modules.bigvgan import Generator
+    from svc_inference_pipeline_b200.utils.util import JsonHParams
+
+    model = Generator(JsonHParams(**cfgd), precision=precision)
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    return model.to(DEV).eval()
+
+
+@pytest.fixture(scope="module")
+def repo_model():
+    from svc_inference_pipeline_b200.utils import synth
+
+    sd = synth.synthetic_state_dict(REPO, seed=0)
+    return build(REPO, sd, "fp32")
+
+
+@pytest.mark.parametrize("tag", list(TINY_VARIANTS))
+@pytest.mark.parametrize("precision", ["fp32_simt", "fp32"])
+def test_tiny_generator_golden(golden, tag, precision):
+    g = golden("tiny_generator.npz")
+    cfgd, sd = tiny_cfg_sd(tag)
+    model = build(cfgd, sd, precision)
+    y = model(torch.from_numpy(g[tag + "_mel"]).to(DEV)).cpu().numpy()
+    assert y.shape == g[tag + "_y"].shape
+    tol = 2e-5 if precision == "fp32_simt" else 1e-4
+    assert np.abs(y - g[tag + "_y_f64"]).max() < tol
+    assert np.abs(y - g[tag + "_y"]).max() < tol
+
+
+def test_tiny_generator_bf16(golden):
+    g = golden("tiny_generator.npz")
+    cfgd, sd = tiny_cfg_sd("b1_snakebeta_log")
+    model = build(cfgd, sd, "bf16")
+    y = model(torch.from_numpy(g["b1_snakebeta_log_mel"]).to(DEV)).cpu().numpy()
+    assert snr_db(g["b1_snakebeta_log_y_f64"], y) > 35.0
+
+
+def test_repo_generator_fp32(golden, repo_model):
+    """BASELINE north_star gate: fp32 path within 1e-4 max-abs of the reference waveform."""
+    g = golden("repo_generator.npz")
+    for tag in ("logmel", "randn"):
+        y = repo_model(torch.from_numpy(g[tag + "_mel"]).to(DEV)).cpu().numpy()
+        assert y.shape == g[tag + "_y"].shape
+        err = np.abs(y - g[tag + "_y"]).max()
+        err64 = np.abs(y - g[tag + "_y_f64"]).max()
+        print(f"repo fp32 {tag}: max-abs vs ref fp32 {err:.3e}, vs ref fp64 {err64:.3e}, SNR {snr_db(g[tag + '_y_f64'], y):.1f} dB")
+        assert err < 1e-4 and err64 < 1e-4
+        assert np.abs(y).max() <= 1.0
+
+
+def test_repo_generator_simt_exact(golden, repo_model):
+    g = golden("repo_generator.npz")
+    repo_model.set_precision("fp32_simt")
+    try:
+        y = repo_model(torch.from_numpy(g["logmel_mel"]).to(DEV)).cpu().numpy()
+    finally:
+        repo_model.set_precision("fp32")
+    assert np.abs(y - g["logmel_y_f64"]).max() < 2e-5
+
+
+def log_mel_l1(ref, y, fs=24000, n_fft=1024, hop=256, n_mels=100):
+    """L1 distance of log-mel spectrograms (HiFi-GAN style analysis: hann window, magnitude,
+    triangular mel bank, log clip 1e-5), after reference utils/mel.py:130-174."""
+    def mel(w):
+        w = torch.from_numpy(np.asarray(w, np.float32)).reshape(-1)
+        spec = torch.stft(w, n_fft, hop_length=hop, win_length=n_fft, window=torch.hann_window(n_fft), center=True, return_complex=True).abs()
+        # triangular filters on the HTK-free "slaney-like" linear-to-mel warp; the same bank is used
+        # for both signals, so only the difference matters
+        freqs = torch.linspace(0, fs / 2, n_fft // 2 + 1)
+        mels = torch.linspace(0, 2595 * np.log10(1 + (fs / 2) / 700), n_mels + 2)
+        hz = 700 * (10 ** (mels / 2595) - 1)
+        fb = torch.zeros(n_mels, n_fft // 2 + 1)
+        for i in range(n_mels):
+            lo, ce, hi = hz[i], hz[i + 1], hz[i + 2]
+            fb[i] = torch.clamp(torch.minimum((freqs - lo) / (ce - lo), (hi - freqs) / (hi - ce)), min=0)
+        return torch.log(torch.clamp(fb @ spec, min=1e-5))
+    return float((mel(ref) - mel(y)).abs().mean())
+
+
+def test_repo_generator_bf16(golden, repo_model):
+    """BASELINE north_star gate: bf16 path >= 35 dB waveform SNR and log-mel L1 <= 1e-2."""
+    g = golden("repo_generator.npz")
+    repo_model.set_precision("bf16")
+    try:
+        for tag in ("logmel", "randn"):
+            y = repo_model(torch.from_numpy(g[tag + "_mel"]).to(DEV)).cpu().numpy()
+            ref = g[tag + "_y_f64"]
+            snr = snr_db(ref, y)
+            l1 = np.mean([log_mel_l1(ref[b, 0], y[b, 0]) for b in range(ref.shape[0])])
+            print(f"repo bf16 {tag}: SNR {snr:.1f} dB, log-mel L1 {l1:.2e}, max-abs {np.abs(y - ref).max():.3e}")
+            assert snr >= 35.0
+            assert l1 <= 1e-2
+    finally:
+        repo_model.set_precision("fp32")
+
+
+def test_v2_generator_fp32(golden):
+    from svc_inference_pipeline_b200.utils import synth
+
+    g = golden("v2_generator.npz")
+    model = build(V2, synth.synthetic_state_dict(V2, seed=0), "fp32")
+    assert sum(p.numel() for p in model.parameters()) == int(g["n_params"]) == 122_184_530
+    y = model(torch.from_numpy(g["logmel_mel"]).to(DEV)).cpu().numpy()
+    assert np.abs(y - g["logmel_y_f64"]).max() < 1e-4
+
+
+def test_batch_and_length_independence(repo_model):
+    """Size-independent properties at larger shapes: batch items are independent, and a chunk with a
+    >= 38-frame halo reproduces the interior of the full forward (receptive field)."""
+    from svc_inference_pipeline_b200.utils import synth
+
+    mel = torch.from_numpy(synth.synthetic_mel(3, 100, 300, seed=77)).to(DEV)
+    full = repo_model(mel)
+    single = repo_model(mel[1:2].contiguous())
+    assert (full[1:2] - single).abs().max().item() < 2e-6
+    lo, hi, halo = 100, 200, 48
+    part = repo_model(mel[:1, :, lo - halo : hi + halo].contiguous())
+    a = full[0, 0, lo * 256 : hi * 256]
+    b = part[0, 0, halo * 256 : (halo + hi - lo) * 256]
+    assert (a - b).abs().max().item() < 5e-6
+    assert torch.isfinite(full).all() and full.abs().max().item() <= 1.0
+
+
+def test_synthesis_audios_and_loader(golden, tmp_path):
+    """The three reference call sites end to end: checkpoint file -> vocoder_model_loader ->
+    synthesis_audios, compared with the reference's own output for the same checkpoint + mel."""
+    from svc_inference_pipeline_b200.modules.bigvgan_inference import synthesis_audios, vocoder_inference
+    from svc_inference_pipeline_b200.utils.load_models import vocoder_model_loader
+    from svc_inference_pipeline_b200.utils.util import JsonHParams
+
+    g = golden("tiny_generator.npz")
+    cfgd, sd = tiny_cfg_sd("b1_snakebeta_log")
+    ckpt = {"generator_state_dict": {"module." + k: torch.from_numpy(v) for k, v in sd.items()}}
+    path = os.path.join(tmp_path, "vocoder.pt")
+    torch.save(ckpt, path)
+    cfg = JsonHParams(device="cuda", vocoder_model_path=path, hop_length=8, vocoder=cfgd)
+    model = vocoder_model_loader(cfg)
+    assert not model.training and next(model.parameters()).is_cuda
+    assert model.load_report == {"missing": [], "wrong_shape": [], "unknown": []}
+    mel = torch.from_numpy(g["synth_mel"]).to(DEV)
+    audio = synthesis_audios(model, mel, cfg)
+    assert isinstance(audio, np.ndarray) and audio.dtype == np.float32 and audio.shape == g["synth_audio"].shape
+    assert np.abs(audio - g["synth_audio"]).max() < 1e-4
+    assert audio[-1] == 0.0
+    out = vocoder_inference(cfg, model, torch.from_numpy(g["synth_mel"])[None], torch.device(DEV))
+    assert out.device.type == "cpu" and np.abs(out.numpy() - g["voc_inf"]).max() < 1e-4
+    with pytest.raises(RuntimeError):
+        synthesis_audios(model, mel[:, :10], cfg)  # < 20 frames: same failure mode as the reference
+
+
+def test_cuda_graph_matches_eager(golden):
+    g = golden("tiny_generator.npz")
+    cfgd, sd = tiny_cfg_sd("b1_snakebeta_log")
+    model = build(cfgd, sd, "fp32")
+    mel = torch.from_numpy(g["b1_snakebeta_log_mel"]).to(DEV)
+    y0 = model(mel)
+    model.use_cuda_graph = True
+    y1 = model(mel)
+    y2 = model(mel * 0.5)
+    model.use_cuda_graph = False
+    y3 = model(mel * 0.5)
+    assert torch.equal(y0, y1) and torch.equal(y2, y3)

@@ -1,0 +1,316 @@
+"""Op-level parity of the CUDA kernels (through the C ABI) against the CPU oracle and the
+reference-generated golden vectors.  Needs a B200: run with ``-m gpu``."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import bigvgan_oracle as O
+from util_cases import bf16_round
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from svc_inference_pipeline_b200 import _lib as L
+    from svc_inference_pipeline_b200 import ops as _ops
+
+    L.check(L.lib().bvg_device_check(0), "device_check")
+    return _ops, L
+
+
+def cl(x):  # [B, C, L] numpy -> channels-last cuda tensor
+    return torch.from_numpy(np.ascontiguousarray(np.transpose(x, (0, 2, 1)))).to(DEV)
+
+
+def cf(t):  # channels-last cuda tensor -> [B, C, L] numpy
+    return np.transpose(t.cpu().numpy(), (0, 2, 1))
+
+
+def snake_params(alpha, beta, logscale):
+    a = np.exp(alpha) if logscale else alpha
+    b = a if beta is None else (np.exp(beta) if logscale else beta)
+    return torch.from_numpy(a.astype(np.float32)).to(DEV), torch.from_numpy((1.0 / (b.astype(np.float32) + np.float32(1e-9))).astype(np.float32)).to(DEV)
+
+
+# ------------------------------------------------------------------------------------------
+# K-A fused Activation1d
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["snake", "snakebeta"])
+@pytest.mark.parametrize("scale", ["lin", "log"])
+@pytest.mark.parametrize("fast_sin", [False, True])
+def test_amp_golden(ops, golden, name, scale, fast_sin):
+    _ops, L = ops
+    g = golden("activation1d.npz")
+    f = golden("filters.npz")["aa12"]
+    log = scale == "log"
+    alpha = g["alpha"] if log else (1.0 + 0.3 * g["alpha"]).astype(np.float32)
+    beta = None if name == "snake" else (g["beta"] if log else (1.0 + 0.3 * g["beta"]).astype(np.float32))
+    a, invb = snake_params(alpha, beta, log)
+    y = cf(_ops.activation1d(cl(g["x"]), a, invb, f, f, fast_sin=fast_sin))
+    np.testing.assert_allclose(y, g[f"{name}_{scale}_a1d"], atol=8e-6, rtol=2e-6)
+    np.testing.assert_allclose(y, g[f"{name}_{scale}_a1d_f64"], atol=8e-6, rtol=2e-6)
+
+
+@pytest.mark.parametrize("ln", [1, 2, 3, 5, 6, 11, 12, 13])
+def test_amp_edges(ops, golden, ln):
+    _ops, L = ops
+    g = golden("activation1d.npz")
+    f = golden("filters.npz")["aa12"]
+    a, invb = snake_params(g["alpha"][:3], g["beta"][:3], True)
+    y = cf(_ops.activation1d(cl(g[f"edge{ln}_x"]), a, invb, f, f))
+    np.testing.assert_allclose(y, g[f"edge{ln}_y"], atol=1e-5, rtol=2e-6)
+
+
+def test_amp_large_argument(ops, golden):
+    _ops, L = ops
+    g = golden("activation1d.npz")
+    f = golden("filters.npz")["aa12"]
+    a, invb = snake_params(g["big_alpha"], g["big_beta"], True)
+    ref64 = O.activation1d(g["big_x"].astype(np.float64), g["big_alpha"].astype(np.float64), g["big_beta"].astype(np.float64), True, f.astype(np.float64), f.astype(np.float64))
+    for fast in (False, True):
+        y = cf(_ops.activation1d(cl(g["big_x"]), a, invb, f, f, fast_sin=fast))
+        # |a*u| reaches ~1e2: fp32 rounding of the product alone moves the phase by ~1e-5
+        assert np.abs(y - ref64).max() < 3e-4, (fast, np.abs(y - ref64).max())
+        assert np.abs(y - g["big_y"]).max() < 3e-4
+
+
+@pytest.mark.parametrize("shape", [(2, 24, 1000), (1, 768, 301), (3, 6, 97), (2, 5, 64), (1, 48, 2500)])
+@pytest.mark.parametrize("vec", [0, 1, 2, 4])
+def test_amp_shapes_vs_oracle(ops, shape, vec):
+    """Ragged lengths, every vector width, chunk boundaries (the time loop is chunked per thread)."""
+    _ops, L = ops
+    B, Ch, Ln = shape
+    if vec and Ch % vec:
+        pytest.skip("channel count not divisible")
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal(shape) * 1.5).astype(np.float32)
+    alpha = (rng.standard_normal(Ch) * 0.3).astype(np.float32)
+    beta = (rng.standard_normal(Ch) * 0.3).astype(np.float32)
+    f = golden_taps()
+    a, invb = snake_params(alpha, beta, True)
+    ref = O.activation1d(x.astype(np.float64), alpha.astype(np.float64), beta.astype(np.float64), True, f.astype(np.float64), f.astype(np.float64))
+    L.set_tuning("amp_vec", vec)
+    try:
+        for chunk in (0, 1, 2):
+            L.set_tuning("amp_chunk", chunk)
+            y = cf(_ops.activation1d(cl(x), a, invb, f, f))
+            assert np.abs(y - ref).max() < 1e-5, (chunk, np.abs(y - ref).max())
+    finally:
+        L.set_tuning("amp_vec", 0)
+        L.set_tuning("amp_chunk", 0)
+
+
+def golden_taps():
+    from svc_inference_pipeline_b200.utils import synth
+
+    return synth.aa_filter_taps()
+
+
+@pytest.mark.parametrize("in_dt,out_dt", [(0, 1), (0, 2), (1, 0), (1, 1), (1, 2)])
+def test_amp_formats(ops, in_dt, out_dt):
+    """bf16 / split element formats: the kernel computes in fp32 on the values it reads, and the
+    stored value is the rounding of the fp32 result."""
+    _ops, L = ops
+    rng = np.random.default_rng(6)
+    x = (rng.standard_normal((2, 48, 517)) * 1.5).astype(np.float32)
+    alpha = (rng.standard_normal(48) * 0.3).astype(np.float32)
+    beta = (rng.standard_normal(48) * 0.3).astype(np.float32)
+    f = golden_taps()
+    a, invb = snake_params(alpha, beta, True)
+    x_seen = bf16_round(x) if in_dt == L.BF16 else x
+    ref = O.activation1d(x_seen.astype(np.float64), alpha.astype(np.float64), beta.astype(np.float64), True, f.astype(np.float64), f.astype(np.float64))
+    y = cf(_ops.activation1d(cl(x), a, invb, f, f, in_dtype=in_dt, out_dtype=out_dt, fast_sin=True))
+    if out_dt == L.BF16:
+        assert np.abs(y - ref).max() <= np.abs(ref).max() * 2**-8 + 1e-5
+        np.testing.assert_array_equal(y, bf16_round(y))
+    elif out_dt == L.SPLIT:
+        assert np.abs(y - ref).max() <= np.abs(ref).max() * 2**-15 + 1e-5
+    else:
+        assert np.abs(y - ref).max() < 2e-5
+
+
+# ------------------------------------------------------------------------------------------
+# K-C / K-T convolutions
+# ------------------------------------------------------------------------------------------
+def _conv_case(golden, tag, transposed):
+    g = golden("convs.npz")
+    return {k: g[f"{tag}_{k}"] for k in ("x", "v", "g", "b", "y", "w", "args")}
+
+
+def _run_conv(ops, c, transposed, backend, split, x_override=None):
+    _ops, L = ops
+    args = [int(a) for a in c["args"]]
+    if transposed:
+        cin, cout, k, u = args
+        kw = dict(transposed=True, stride=u, padding=(k - u) // 2)
+    else:
+        ch, k, d = args
+        cin = cout = ch
+        kw = dict(dilation=d, padding=O.get_padding(k, d))
+    v, gg, b = (torch.from_numpy(c[n]).to(DEV) for n in ("v", "g", "b"))
+    pc = _ops.pack_conv(v, gg, b, backend=backend, split=split, **kw)
+    x = c["x"] if x_override is None else x_override
+    xc = cl(x)
+    if xc.shape[-1] != pc.x_pitch:  # zero-pad channels up to the pitch the backend expects
+        xc = torch.nn.functional.pad(xc, (0, pc.x_pitch - xc.shape[-1]))
+    y = _ops.conv(xc.contiguous(), pc)
+    B, Ln, n = y.shape
+    if transposed:
+        y = y.reshape(B, Ln * u, cout)
+    return cf(y)
+
+
+@pytest.mark.parametrize("tag", ["c8k3d1", "c8k7d3", "c6k11d5", "c4k11d5_short"])
+def test_conv_simt_golden(ops, golden, tag):
+    c = _conv_case(golden, tag, False)
+    y = _run_conv(ops, c, False, 0, False)
+    np.testing.assert_allclose(y, c["y"], atol=5e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("tag", ["t8to4k8u4", "t6to3k4u2", "t4to2k16u8", "t4to2k4u2_len1"])
+def test_convT_simt_golden(ops, golden, tag):
+    c = _conv_case(golden, tag, True)
+    y = _run_conv(ops, c, True, 0, False)
+    assert y.shape == c["y"].shape
+    np.testing.assert_allclose(y, c["y"], atol=5e-6, rtol=1e-5)
+
+
+def _oracle_conv(x, v, g, b, transposed, k, d=1, u=1):
+    w = O.weight_norm_fold(v.astype(np.float64), g.astype(np.float64))
+    if transposed:
+        return O.conv_transpose1d(x.astype(np.float64), w, b.astype(np.float64), u, (k - u) // 2), w
+    return O.conv1d(x.astype(np.float64), w, b.astype(np.float64), d, O.get_padding(k, d)), w
+
+
+UMMA_CONV_CASES = [
+    # (B, C, L, k, d)
+    (2, 64, 300, 3, 1),
+    (1, 128, 517, 7, 3),
+    (2, 192, 260, 11, 5),
+    (1, 96, 400, 11, 1),
+    (2, 48, 333, 7, 5),
+    (3, 24, 1000, 11, 5),
+    (1, 24, 50, 3, 1),
+    (1, 768, 140, 3, 1),
+    (1, 384, 129, 7, 1),
+    (2, 8, 77, 3, 3),
+]
+
+
+def _umma_conv_check(ops, B, Ch, Ln, k, d, split, a_mode, desc_mode):
+    _ops, L = ops
+    rng = np.random.default_rng(100 + Ch + k + d)
+    x = rng.standard_normal((B, Ch, Ln)).astype(np.float32)
+    v = (rng.standard_normal((Ch, Ch, k)) / np.sqrt(Ch * k)).astype(np.float32)
+    g = (np.sqrt((v.astype(np.float64) ** 2).sum(axis=(1, 2), keepdims=True)) * rng.uniform(0.7, 1.4, (Ch, 1, 1))).astype(np.float32)
+    b = (rng.standard_normal(Ch) * 0.1).astype(np.float32)
+    L.set_tuning("umma_a_mode", a_mode)
+    L.set_tuning("umma_desc_mode", desc_mode)
+    try:
+        pc = _ops.pack_conv(*(torch.from_numpy(t).to(DEV) for t in (v, g, b)), dilation=d, padding=O.get_padding(k, d), backend=L.UMMA, split=split)
+        y = cf(_ops.conv(cl(x), pc))
+    finally:
+        L.set_tuning("umma_a_mode", 1)
+        L.set_tuning("umma_desc_mode", 0)
+    ref, w = _oracle_conv(x, v, g, b, False, k, d=d)
+    if split:
+        err = np.abs(y - ref).max()
+        assert err < 3e-5 * max(1.0, np.abs(ref).max()), f"split err {err}"
+    else:
+        # exact emulation: bf16 operands, wide accumulation
+        wq = bf16_round(w.astype(np.float32)).astype(np.float64)
+        refq = O.conv1d(bf16_round(x).astype(np.float64), wq, b.astype(np.float64), d, O.get_padding(k, d))
+        err = np.abs(y - refq).max()
+        assert err < 2e-3, f"bf16 err vs bf16-emulated oracle {err}"
+        assert np.abs(y - ref).max() < 0.05 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("case", UMMA_CONV_CASES)
+def test_conv_umma_per_tap(ops, case):
+    """A operand loaded once per tap (no descriptor row offsets): the conservative mode."""
+    _umma_conv_check(ops, *case, split=False, a_mode=0, desc_mode=0)
+
+
+@pytest.mark.parametrize("case", UMMA_CONV_CASES)
+def test_conv_umma_halo(ops, case):
+    """A operand loaded once per Cin slice, taps addressed by row-shifted UMMA descriptors."""
+    _umma_conv_check(ops, *case, split=False, a_mode=1, desc_mode=0)
+
+
+@pytest.mark.parametrize("case", UMMA_CONV_CASES[:6])
+def test_conv_umma_split(ops, case):
+    _umma_conv_check(ops, *case, split=True, a_mode=1, desc_mode=0)
+
+
+@pytest.mark.parametrize("cin,cout,k,u,Ln", [(64, 32, 8, 4, 50), (128, 64, 4, 2, 333), (48, 24, 4, 2, 200), (256, 128, 16, 8, 40), (1536, 768, 8, 4, 20)])
+@pytest.mark.parametrize("split", [False, True])
+def test_convT_umma(ops, cin, cout, k, u, Ln, split):
+    _ops, L = ops
+    rng = np.random.default_rng(cin + k)
+    x = rng.standard_normal((2, cin, Ln)).astype(np.float32)
+    v = (rng.standard_normal((cin, cout, k)) / np.sqrt(cin * k / u)).astype(np.float32)
+    g = (np.sqrt((v.astype(np.float64) ** 2).sum(axis=(1, 2), keepdims=True)) * rng.uniform(0.7, 1.4, (cin, 1, 1))).astype(np.float32)
+    b = (rng.standard_normal(cout) * 0.1).astype(np.float32)
+    pc = _ops.pack_conv(*(torch.from_numpy(t).to(DEV) for t in (v, g, b)), transposed=True, stride=u, padding=(k - u) // 2, backend=L.UMMA, split=split)
+    y = _ops.conv(cl(x), pc)
+    y = cf(y.reshape(2, Ln * u, cout))
+    ref, w = _oracle_conv(x, v, g, b, True, k, u=u)
+    assert y.shape == ref.shape
+    if split:
+        assert np.abs(y - ref).max() < 3e-5 * max(1.0, np.abs(ref).max())
+    else:
+        wq = bf16_round(w.astype(np.float32)).astype(np.float64)
+        refq = O.conv_transpose1d(bf16_round(x).astype(np.float64), wq, b.astype(np.float64), u, (k - u) // 2)
+        assert np.abs(y - refq).max() < 2e-3
+
+
+def test_conv_epilogue_variants(ops):
+    """residual add, running-sum add, division and every output format, on both backends."""
+    _ops, L = ops
+    rng = np.random.default_rng(9)
+    B, Ch, Ln, k, d = 2, 64, 203, 7, 3
+    x = rng.standard_normal((B, Ch, Ln)).astype(np.float32)
+    res = rng.standard_normal((B, Ch, Ln)).astype(np.float32)
+    acc = rng.standard_normal((B, Ch, Ln)).astype(np.float32)
+    v = (rng.standard_normal((Ch, Ch, k)) / np.sqrt(Ch * k)).astype(np.float32)
+    g = np.sqrt((v.astype(np.float64) ** 2).sum(axis=(1, 2), keepdims=True)).astype(np.float32)
+    b = (rng.standard_normal(Ch) * 0.1).astype(np.float32)
+    ref, _ = _oracle_conv(x, v, g, b, False, k, d=d)
+    want = (ref + res + acc) / 3.0
+    for backend, split, tol in ((L.SIMT, False, 1e-5), (L.UMMA, True, 5e-5)):
+        pc = _ops.pack_conv(*(torch.from_numpy(t).to(DEV) for t in (v, g, b)), dilation=d, padding=O.get_padding(k, d), backend=backend, split=split)
+        for out_dt, otol in ((L.F32, 0.0), (L.BF16, 2**-8), (L.SPLIT, 2**-15)):
+            y = cf(_ops.conv(cl(x), pc, out_dtype=out_dt, res=cl(res), acc=cl(acc), div=3.0))
+            assert np.abs(y - want).max() < tol + otol * np.abs(want).max(), (backend, out_dt, np.abs(y - want).max())
+        y = cf(_ops.conv(cl(x), pc, res=cl(res), res_dtype=L.BF16))
+        assert np.abs(y - (ref + bf16_round(res))).max() < tol
+
+
+# ------------------------------------------------------------------------------------------
+# head / tail
+# ------------------------------------------------------------------------------------------
+def test_pack_mel(ops):
+    _ops, L = ops
+    rng = np.random.default_rng(3)
+    mel = rng.standard_normal((3, 100, 77)).astype(np.float32)
+    for dt, tol in ((L.F32, 0), (L.BF16, 2**-8), (L.SPLIT, 2**-15)):
+        y = _ops.pack_mel(torch.from_numpy(mel).to(DEV), 104, dt).cpu().numpy()
+        assert y.shape == (3, 77, 104)
+        assert np.abs(y[:, :, :100] - np.transpose(mel, (0, 2, 1))).max() <= tol * np.abs(mel).max()
+        assert np.all(y[:, :, 100:] == 0)
+
+
+def test_post(ops):
+    _ops, L = ops
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal((2, 24, 999)).astype(np.float32)
+    v = (rng.standard_normal((1, 24, 7)) * 0.1).astype(np.float32)
+    g = np.array([[[1.7]]], dtype=np.float32)
+    b = np.array([0.05], dtype=np.float32)
+    w = O.weight_norm_fold(v.astype(np.float64), g.astype(np.float64))
+    ref = np.tanh(O.conv1d(x.astype(np.float64), w, b.astype(np.float64), 1, 3))[:, 0]
+    y = _ops.post(cl(x), *(torch.from_numpy(t).to(DEV) for t in (v, g, b))).cpu().numpy()
+    assert np.abs(y - ref).max() < 2e-6

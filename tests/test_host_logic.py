@@ -1,0 +1,161 @@
+"""Host-side logic that needs no GPU: config reader, checkpoint filter, state_dict grammar,
+C-ABI symbol/struct checks, conv geometry tables."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from util_cases import REPO, TINY, V2
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_json5_subset_reader(tmp_path):
+    from svc_inference_pipeline_b200.utils.util import JsonHParams, load_config, loads_json5_subset
+
+    text = '{\n // comment\n "a": 1, /* block */ "s": "http://x//y", "l": [1, 2, 3,], "d": {"k": true,},\n}'
+    d = loads_json5_subset(text)
+    assert d == {"a": 1, "s": "http://x//y", "l": [1, 2, 3], "d": {"k": True}}
+    cfg = load_config(os.path.join(ROOT, "svc_inference_pipeline_b200", "config", "config.json"))
+    assert isinstance(cfg, JsonHParams) and cfg.hop_length == 256 and cfg.vocoder.upsample_rates == [4, 4, 2, 2, 2, 2]
+    assert "vocoder" in cfg and cfg["vocoder"].activation == "snakebeta" and len(cfg.vocoder) == 9
+    assert int(np.prod(cfg.vocoder.upsample_rates)) == cfg.hop_length
+
+
+def test_basic_config_inheritance(tmp_path, monkeypatch):
+    from svc_inference_pipeline_b200.utils.util import load_config
+
+    (tmp_path / "base.json").write_text('{"a": 1, "v": {"x": 1, "y": 2}}')
+    (tmp_path / "child.json").write_text('{"basic_config": "base.json", "v": {"y": 3}, "b": 2,}')
+    monkeypatch.setenv("WORD_DIR", str(tmp_path))
+    cfg = load_config(str(tmp_path / "child.json"))
+    assert cfg.a == 1 and cfg.b == 2 and cfg.v.x == 1 and cfg.v.y == 3
+
+
+def test_generator_structure_matches_reference_grammar():
+    from svc_inference_pipeline_b200.modules.bigvgan import Generator
+    from svc_inference_pipeline_b200.utils import synth
+    from svc_inference_pipeline_b200.utils.util import JsonHParams
+
+    for cfgd, n_params in ((TINY, None), (REPO, 112_446_290), (V2, 122_184_530)):
+        model = Generator(JsonHParams(**cfgd))
+        spec = synth.state_dict_spec(cfgd)
+        sd = model.state_dict()
+        assert list(sd.keys()) == list(spec.keys())
+        assert all(tuple(sd[k].shape) == spec[k][0] for k in sd)
+        if n_params:
+            assert sum(p.numel() for p in model.parameters()) == n_params
+            assert len(sd) == 784
+    with pytest.raises(NotImplementedError):
+        Generator(JsonHParams(**dict(TINY, activation="relu")))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        Generator(JsonHParams(**TINY))(torch.zeros(1, 10, 8))
+
+
+def test_default_init_matches_weight_norm_identity():
+    from svc_inference_pipeline_b200.modules.bigvgan import Generator
+    from svc_inference_pipeline_b200.utils.util import JsonHParams
+
+    m = Generator(JsonHParams(**TINY))
+    v, g = m.ups[0][0].weight_v, m.ups[0][0].weight_g
+    assert g.shape == (32, 1, 1)  # ConvTranspose1d: dim 0 is Cin
+    torch.testing.assert_close(g.flatten(), v.flatten(1).norm(dim=1))
+    assert float(m.resblocks[0].activations[0].act.alpha.abs().max()) == 0.0  # log-scale init
+    # remove_weight_norm keeps the folded weight
+    w_before = v * (g / v.flatten(1).norm(dim=1).reshape(-1, 1, 1))
+    m.remove_weight_norm()
+    torch.testing.assert_close(m.ups[0][0].weight_v, w_before)
+
+
+def test_checkpoint_filter_and_loader_cpu(tmp_path):
+    from svc_inference_pipeline_b200.utils import synth
+    from svc_inference_pipeline_b200.utils.load_models import filter_state_dict, vocoder_model_loader
+    from svc_inference_pipeline_b200.utils.util import JsonHParams
+
+    sd = synth.synthetic_state_dict(TINY, seed=3)
+    ckpt = {"module." + k: torch.from_numpy(v) for k, v in sd.items()}
+    ckpt["module.conv_pre.bias"] = torch.zeros(7)  # wrong shape -> dropped, keeps init
+    ckpt["module.not_a_key"] = torch.zeros(1)
+    del ckpt["module.conv_post.bias"]
+    path = str(tmp_path / "v.pt")
+    torch.save({"generator_state_dict": ckpt}, path)
+    cfg = JsonHParams(device="cpu", vocoder_model_path=path, hop_length=8, vocoder=dict(TINY))
+    with pytest.warns(UserWarning):
+        model = vocoder_model_loader(cfg)
+    rep = model.load_report
+    assert rep["unknown"] == ["not_a_key"]
+    assert [w[0] for w in rep["wrong_shape"]] == ["conv_pre.bias"]
+    assert set(rep["missing"]) == {"conv_pre.bias", "conv_post.bias"}
+    assert not model.training and next(model.parameters()).device.type == "cpu"
+    np.testing.assert_array_equal(model.state_dict()["ups.0.0.weight_v"].numpy(), sd["ups.0.0.weight_v"])
+    kept, _ = filter_state_dict({"module.conv_pre.weight_g": torch.zeros(32, 1, 1)}, model.state_dict())
+    assert list(kept) == ["conv_pre.weight_g"]
+    # a folded ".weight" checkpoint (saved after remove_weight_norm) is accepted too
+    folded = {k: torch.from_numpy(v) for k, v in sd.items() if not k.startswith("conv_pre.weight")}
+    v, g = sd["conv_pre.weight_v"], sd["conv_pre.weight_g"]
+    w = v * (g / np.sqrt((v**2).sum(axis=(1, 2), keepdims=True)))
+    folded["conv_pre.weight"] = torch.from_numpy(w)
+    model.load_state_dict(folded)
+    torch.testing.assert_close(model.conv_pre.weight_v.detach(), torch.from_numpy(w))
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "bvg_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(bvg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_capi_exports_every_declared_symbol():
+    from svc_inference_pipeline_b200 import _lib as L
+
+    lib = L.lib()  # raises if the .so is missing: there is no fallback
+    names = header_functions()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/bvg_b200.h but not exported"
+    assert sorted(L.EXPORTS) == names
+    assert lib.bvg_abi_version() == 1
+    assert lib.bvg_sizeof_op() == C.sizeof(L.Op)
+    assert lib.bvg_sizeof_conv_weights() == C.sizeof(L.ConvWeights)
+
+
+def test_conv_geometry_tables():
+    from svc_inference_pipeline_b200 import _lib as L
+
+    lib = L.lib()
+
+    def geom(*a):
+        g, w = L.ConvGeom(*a), L.ConvWeights()
+        L.check(lib.bvg_conv_geometry(C.byref(g), C.byref(w)))
+        return w
+
+    w = geom(0, 768, 768, 11, 5, 1, 25, L.UMMA, 1, 0)
+    assert (w.n_total, w.n_tile, w.n_tiles, w.cin_pad, w.x_pitch, w.tap_stride) == (768, 256, 3, 768, 768, 11)
+    assert list(w.shift[2])[:11] == [5 * (j - 5) for j in range(11)]
+    w = geom(1, 1536, 768, 8, 1, 4, 2, L.UMMA, 0, 0)  # ups.0: phase r uses taps {-1,0} (r<2) or {0,1}
+    assert (w.n_total, w.n_tile, w.n_tiles, w.tap_stride) == (3072, 256, 12, 2)
+    assert [list(w.shift[t])[:2] for t in (0, 5, 6, 11)] == [[-1, 0], [-1, 0], [0, 1], [0, 1]]
+    w = geom(1, 48, 24, 4, 1, 2, 1, L.UMMA, 0, 0)  # narrow: one tile spans both phases -> 3 taps
+    assert (w.n_total, w.n_tile, w.n_tiles, w.n_taps[0]) == (48, 48, 1, 3)
+    w = geom(0, 100, 1536, 7, 1, 1, 3, L.UMMA, 0, 0)
+    assert (w.cin_pad, w.x_pitch, w.n_tiles) == (128, 104, 6)
+    w = geom(0, 100, 1536, 7, 1, 1, 3, L.SIMT, 0, 0)
+    assert (w.cin_pad, w.x_pitch, w.n_tile, w.n_tiles) == (100, 100, 64, 24)
+    w = geom(1, 768, 384, 16, 1, 8, 4, L.SIMT, 0, 0)
+    assert w.n_taps[0] == 3 and list(w.shift[0])[:3] == [-1, 0, 1]
+    g = L.ConvGeom(0, 8, 8, 40, 1, 1, 0, L.SIMT, 0, 0)
+    assert lib.bvg_conv_geometry(C.byref(g), C.byref(L.ConvWeights())) != 0
+    assert b"BVG_MAX_TAPS" in lib.bvg_last_error()
+
+
+def test_no_product_import_of_oracle():
+    """The oracle is test infrastructure: nothing under the package may import it."""
+    pkg = os.path.join(ROOT, "svc_inference_pipeline_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f

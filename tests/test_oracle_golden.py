@@ -6,27 +6,7 @@ import pytest
 from oracle import bigvgan_oracle as O
 from svc_inference_pipeline_b200.utils import synth
 
-TINY = {
-    "resblock_kernel_sizes": [3, 7],
-    "upsample_rates": [4, 2],
-    "input_dim": 10,
-    "upsample_initial_channel": 32,
-    "resblock": "1",
-    "upsample_kernel_sizes": [8, 4],
-    "resblock_dilation_sizes": [[1, 3, 5], [1, 3, 5]],
-    "activation": "snakebeta",
-    "snake_logscale": True,
-}
-TINY_VARIANTS = {
-    "b1_snakebeta_log": dict(),
-    "b2_snake_lin": dict(resblock="2", activation="snake", snake_logscale=False, resblock_dilation_sizes=[[1, 3], [1, 3]]),
-    "b1_snake_log": dict(activation="snake"),
-    "b2_snakebeta_lin": dict(resblock="2", snake_logscale=False, resblock_dilation_sizes=[[1, 3], [1, 3]]),
-}
-REPO = dict(TINY, resblock_kernel_sizes=[3, 7, 11], upsample_rates=[4, 4, 2, 2, 2, 2], input_dim=100,
-            upsample_initial_channel=1536, upsample_kernel_sizes=[8, 8, 4, 4, 4, 4],
-            resblock_dilation_sizes=[[1, 3, 5]] * 3)
-
+from util_cases import REPO, TINY, TINY_VARIANTS  # noqa: E402
 
 def tiny_sd(tag):
     cfg = dict(TINY, **TINY_VARIANTS[tag])
@@ -169,3 +149,21 @@ def test_repo_generator_oracle(golden):
     assert y.shape == (1, 1, 24 * 256)
     assert np.abs(y - g["logmel_y"]).max() < 2e-5
     assert np.abs(y - g["logmel_y_f64"]).max() < 2e-5
+
+
+def test_torch_cpu_port_matches_goldens(golden):
+    """The PyTorch-CPU port used as bench.py's CPU baseline is pinned to the same vectors."""
+    import torch
+
+    from oracle import bigvgan_torch_cpu as P
+
+    g = golden("tiny_generator.npz")
+    for tag in TINY_VARIANTS:
+        cfg, sd = tiny_sd(tag)
+        tsd = {k: torch.from_numpy(v) for k, v in sd.items()}
+        y = P.generator_forward(tsd, cfg, torch.from_numpy(g[tag + "_mel"])).numpy()
+        np.testing.assert_allclose(y, g[tag + "_y"], atol=2e-6)
+    g = golden("repo_generator.npz")
+    tsd = {k: torch.from_numpy(v) for k, v in synth.synthetic_state_dict(REPO, seed=0).items()}
+    y = P.generator_forward(tsd, REPO, torch.from_numpy(g["logmel_mel"])).numpy()
+    assert np.abs(y - g["logmel_y"]).max() < 2e-6
