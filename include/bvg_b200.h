@@ -197,7 +197,8 @@ int bvg_program_create(const bvg_op* ops, int32_t n_ops, bvg_program** out);
 int bvg_program_run(bvg_program* p, void* stream);
 /* Same launches with a CUDA event between consecutive ops; synchronises the stream and returns the
  * device time (ms) and launch count per bvg_op_kind (arrays of 4).  Measurement aid for bench.py. */
-int bvg_program_run_timed(bvg_program* p, void* stream, float* ms_by_kind, int32_t* n_by_kind);
+int bvg_program_run_timed(bvg_program* p, void* stream, float* ms_by_kind, int32_t* n_by_kind,
+                          float* ms_per_op /* optional, n_ops entries */);
 int bvg_program_num_launches(const bvg_program* p);
 void bvg_program_destroy(bvg_program* p);
 

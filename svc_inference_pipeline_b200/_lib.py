@@ -175,7 +175,7 @@ def lib():
         "bvg_pack_post_weights": [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p],
         "bvg_program_create": [C.POINTER(Op), C.c_int32, C.POINTER(C.c_void_p)],
         "bvg_program_run": [C.c_void_p, C.c_void_p],
-        "bvg_program_run_timed": [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)],
+        "bvg_program_run_timed": [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_float)],
         "bvg_program_num_launches": [C.c_void_p],
         "bvg_program_destroy": [C.c_void_p],
     }.items():

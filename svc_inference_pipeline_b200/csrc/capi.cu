@@ -195,7 +195,7 @@ int bvg_program_run(bvg_program* p, void* stream) {
   return BVG_OK;
 }
 
-int bvg_program_run_timed(bvg_program* p, void* stream, float* ms_by_kind, int32_t* n_by_kind) {
+int bvg_program_run_timed(bvg_program* p, void* stream, float* ms_by_kind, int32_t* n_by_kind, float* ms_per_op) {
   if (!p || !ms_by_kind || !n_by_kind) {
     bvg::set_error("program_run_timed: bad argument");
     return BVG_EINVAL;
@@ -220,6 +220,7 @@ int bvg_program_run_timed(bvg_program* p, void* stream, float* ms_by_kind, int32
       float ms = 0.f;
       cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
       const int k = p->ops[i].kind;
+      if (ms_per_op) ms_per_op[i] = ms;
       if (k >= 0 && k < 4) {
         ms_by_kind[k] += ms;
         n_by_kind[k] += 1;

@@ -357,7 +357,13 @@ class Generator(nn.Module):
         cfg = self.cfg
         ops, keep = [], []
 
+        labels = []
+        esz = {L.F32: 4, L.BF16: 2, L.SPLIT: 4}
+
         def conv_op(name, x, out, B_, L_, res=None, acc=None, div=1.0):
+            m = self.get_submodule(name)
+            flops = 2.0 * m.cin * m.cout * m.ksize * B_ * L_
+            labels.append((f"{name} {m.cin}->{m.cout} k{m.ksize} d{m.dilation} u{m.stride} L{L_}", "conv", flops))
             op = L.Op()
             op.kind = L.OP_CONV
             d = op.u.conv
@@ -369,6 +375,7 @@ class Generator(nn.Module):
             ops.append(op)
 
         def amp_op(name, x, y, B_, L_, C_):
+            labels.append((f"{name} C{C_} L{L_}", "amp", float(B_) * L_ * C_ * (esz[x.dtype] + esz[y.dtype])))
             a, invb, up, down = pk["act"][name]
             op = L.Op()
             op.kind = L.OP_AMP
@@ -404,6 +411,7 @@ class Generator(nn.Module):
         out = torch.empty(B, 1, lens[-1], dtype=torch.float32, device=dev)
         keep += [mel_in, melp, h, h2, x_in, xa, xs, t_op, t_mid, y_post, out]
 
+        labels.append(("pack_mel", "pack", 0.0))
         op = L.Op()
         op.kind = L.OP_PACK
         op.u.pack.d_mel = mel_in.data_ptr()
@@ -459,7 +467,10 @@ class Generator(nn.Module):
         d.d_out = out.data_ptr()
         d.B, d.L, d.C, d.ksize = B, lens[-1], chans[-1], self.conv_post.ksize
         ops.append(op)
-        return _Program(ops, keep, mel_in, out, len(ops))
+        labels.append(("conv_post+tanh", "post", 0.0))
+        prog = _Program(ops, keep, mel_in, out, len(ops))
+        prog.labels = labels
+        return prog
 
     def _program(self, B: int, T: int) -> _Program:
         key = (B, T, self.precision)
@@ -477,6 +488,24 @@ class Generator(nn.Module):
     def workspace_bytes(self, B: int, T: int) -> int:
         return sum(k.nbytes() if isinstance(k, _Buf) else k.numel() * k.element_size() for k in self._program(B, T).keep)
 
+    def profile_ops(self, B: int, T: int, reps: int = 2):
+        """Per-launch device time of one forward: list of (label, kind, ms, work) where work is
+        algorithmic FLOPs (conv) or bytes (AMP)."""
+        dev = self._require_cuda()
+        prog = self._program(B, T)
+        n = prog.launches
+        per = (C.c_float * n)()
+        ms = (C.c_float * 4)()
+        cnt = (C.c_int32 * 4)()
+        acc = [0.0] * n
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            for _ in range(max(1, reps)):
+                L.check(L.lib().bvg_program_run_timed(prog.handle, stream, ms, cnt, per), "program_run_timed")
+                for i in range(n):
+                    acc[i] += per[i] / max(1, reps)
+        return [(lab, kind, acc[i], work) for i, (lab, kind, work) in enumerate(prog.labels)]
+
     def launches_per_forward(self, B: int, T: int) -> int:
         return self._program(B, T).launches
 
@@ -492,7 +521,7 @@ class Generator(nn.Module):
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             for _ in range(max(1, reps)):
-                L.check(L.lib().bvg_program_run_timed(prog.handle, stream, ms, cnt), "program_run_timed")
+                L.check(L.lib().bvg_program_run_timed(prog.handle, stream, ms, cnt, None), "program_run_timed")
                 for k in range(4):
                     tot[k] += ms[k] / max(1, reps)
         return {
