@@ -32,11 +32,15 @@
 
 namespace bvg {
 
-constexpr int UM_BM = 128;          // rows per tile (TMEM lanes)
+constexpr int UM_BM = 128;          // rows per M block (TMEM lanes)
 constexpr int UM_KB = 64;           // channels per K slice (one 128-byte swizzle row of bf16)
-constexpr int UM_THREADS = 256;
+constexpr int UM_EPI_WARPS = 8;     // two warps per TMEM lane quarter
+constexpr int UM_THREADS = 128 + 32 * UM_EPI_WARPS;
 constexpr int UM_A_STAGES = 2;
 constexpr int UM_MAX_B_STAGES = 8;
+constexpr int UM_MAX_T_STAGES = 4;
+constexpr int UM_MAX_MB = 8;
+constexpr int UM_STAGING_BYTES = UM_EPI_WARPS * 32 * 64;  // 32 rows x 16 fp32 per epilogue warp
 constexpr int UM_SMEM_LIMIT = 227 * 1024;
 
 struct UmmaParams {
@@ -48,11 +52,13 @@ struct UmmaParams {
   int n_tile, n_tiles, tap_stride;
   int n_cb;             // Cin slices
   int cin;              // true input channels (K steps of the last slice)
+  int mb;               // M blocks (of 128 rows) per tile: they share every weight box
+  int tile_rows;        // mb * 128
   int m_tiles_per_item;
   long long total_tiles;
-  int a_rows;           // rows per A box
-  int halo;             // 1: one A box per Cin slice shared by all taps; 0: one box per tap
-  int desc_mode;        // 0: base_offset = 0; 1: base_offset = (addr >> 7) & 7  (HALO row phase)
+  int a_box_rows, a_boxes;  // the A super-tile is loaded as a_boxes TMA boxes of a_box_rows rows
+  int col_stride;       // TMEM columns per accumulator (n_tile rounded up to 32)
+  int t_stages;         // accumulator stages (each mb * col_stride columns)
   int b_stages;
   int a_stage_bytes;    // all planes
   int a_plane_bytes;
@@ -155,6 +161,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&r)[32]) {
       : "r"(addr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(addr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 }  // namespace ptx
@@ -163,13 +178,16 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   [0,14) start address >> 4   [16,30) leading byte offset >> 4 (unused for swizzled K-major)
 //   [32,46) stride byte offset >> 4 = 1024 B between 8-row groups   [46,48) version = 1
 //   [49,52) base offset   [61,64) layout type = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, int desc_mode) {
+// The 128B swizzle is a function of the absolute shared-memory address bits (measured on B200:
+// profiles/r01_probe_first_contact.log, umma_halo0 vs umma_halo1), so a start address advanced by
+// whole 128-byte rows -- not a multiple of the 8-row atom -- with base_offset = 0 addresses the
+// rows TMA wrote.  That is what lets every tap of a dilated conv read one shared A halo tile.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
   uint64_t d = 0;
   d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
   d |= (uint64_t)1 << 16;
   d |= (uint64_t)(1024 >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  if (desc_mode == 1) d |= (uint64_t)((addr >> 7) & 7u) << 49;
   d |= (uint64_t)2 << 61;
   return d;
 }
@@ -181,20 +199,21 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
 
 __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_constant__ UmmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve-up: [A stages][B stages][barriers][tmem ptr]; base rounded up to 1024 B (swizzle atom)
+  // carve-up: [A stages][B stages][epilogue staging][barriers][tmem ptr]; base rounded up to 1024 B
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
   const uint32_t b_base = a_base + UM_A_STAGES * p.a_stage_bytes;
-  const uint32_t bar_base = b_base + p.b_stages * p.b_stage_bytes;
-  // barrier words (8 B each)
+  const uint32_t stg_base = b_base + p.b_stages * p.b_stage_bytes;
+  const uint32_t bar_base = stg_base + UM_STAGING_BYTES;
   auto a_full = [&](int s) { return bar_base + 8u * s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (UM_A_STAGES + s); };
   auto b_full = [&](int s) { return bar_base + 8u * (2 * UM_A_STAGES + s); };
   auto b_empty = [&](int s) { return bar_base + 8u * (2 * UM_A_STAGES + UM_MAX_B_STAGES + s); };
   auto t_full = [&](int s) { return bar_base + 8u * (2 * UM_A_STAGES + 2 * UM_MAX_B_STAGES + s); };
-  auto t_empty = [&](int s) { return bar_base + 8u * (2 * UM_A_STAGES + 2 * UM_MAX_B_STAGES + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * UM_A_STAGES + 2 * UM_MAX_B_STAGES + 4);
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+  auto t_empty = [&](int s) { return bar_base + 8u * (2 * UM_A_STAGES + 2 * UM_MAX_B_STAGES + UM_MAX_T_STAGES + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * UM_A_STAGES + 2 * UM_MAX_B_STAGES + 2 * UM_MAX_T_STAGES);
+  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));  // generic pointer to smem_base
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -216,9 +235,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
       ptx::mbar_init(b_full(s), 1);
       ptx::mbar_init(b_empty(s), 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < p.t_stages; ++s) {
       ptx::mbar_init(t_full(s), 1);
-      ptx::mbar_init(t_empty(s), 4);  // one arrive per epilogue warp
+      ptx::mbar_init(t_empty(s), UM_EPI_WARPS);  // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
     ptx::fence_proxy_async();
@@ -233,27 +252,30 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int planes = p.planes;
+  const int stage_cols = p.mb * p.col_stride;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
       int sa = 0, pa = 0, sb = 0, pb = 0;
+      const int box_bytes = p.a_box_rows * 128;
       for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int nt = (int)(tile % p.n_tiles);
         const long long mt = tile / p.n_tiles;
         const int b = (int)(mt / p.m_tiles_per_item);
-        const int t0 = (int)(mt % p.m_tiles_per_item) * UM_BM;
+        const int t0 = (int)(mt % p.m_tiles_per_item) * p.tile_rows;
         const int ntaps = p.n_taps[nt];
+        const int row0 = t0 + p.min_shift[nt];
         for (int cb = 0; cb < p.n_cb; ++cb) {
+          // A super-tile: rows [row0, row0 + a_boxes * a_box_rows) x 64 channels, every plane
+          ptx::mbar_wait(a_empty(sa), pa ^ 1, p.err_flag, 1);
+          ptx::mbar_expect_tx(a_full(sa), (uint32_t)p.a_stage_bytes);
+          for (int pl = 0; pl < planes; ++pl)
+            for (int bx = 0; bx < p.a_boxes; ++bx)
+              ptx::tma_load_3d(a_base + sa * p.a_stage_bytes + pl * p.a_plane_bytes + bx * box_bytes, &p.tm_x[pl], a_full(sa), cb * UM_KB,
+                               row0 + bx * p.a_box_rows, b);
+          if (++sa == UM_A_STAGES) { sa = 0; pa ^= 1; }
           for (int slot = 0; slot < ntaps; ++slot) {
-            if (!p.halo || slot == 0) {
-              const int row0 = t0 + (p.halo ? p.min_shift[nt] : p.shift[nt][slot]);
-              ptx::mbar_wait(a_empty(sa), pa ^ 1, p.err_flag, 1);
-              ptx::mbar_expect_tx(a_full(sa), (uint32_t)p.a_stage_bytes);
-              for (int pl = 0; pl < planes; ++pl)
-                ptx::tma_load_3d(a_base + sa * p.a_stage_bytes + pl * p.a_plane_bytes, &p.tm_x[pl], a_full(sa), cb * UM_KB, row0, b);
-              if (++sa == UM_A_STAGES) { sa = 0; pa ^= 1; }
-            }
             for (int wp = 0; wp < planes; ++wp) {
               ptx::mbar_wait(b_empty(sb), pb ^ 1, p.err_flag, 2);
               ptx::mbar_expect_tx(b_full(sb), (uint32_t)p.b_stage_bytes);
@@ -275,82 +297,136 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
         const int ntaps = p.n_taps[nt];
         ptx::mbar_wait(t_empty(as), ap ^ 1, p.err_flag, 3);
         ptx::tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(as * 256);
-        uint32_t accumulate = 0;
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(as * stage_cols);
         for (int cb = 0; cb < p.n_cb; ++cb) {
           const int valid = min(UM_KB, p.cin - cb * UM_KB);
           const int ksteps = (valid + 15) >> 4;
-          uint32_t a_stage = 0;
+          ptx::mbar_wait(a_full(sa), pa, p.err_flag, 4);
+          const uint32_t a_stage = a_base + sa * p.a_stage_bytes;
           for (int slot = 0; slot < ntaps; ++slot) {
-            if (!p.halo || slot == 0) {
-              ptx::mbar_wait(a_full(sa), pa, p.err_flag, 4);
-              a_stage = a_base + sa * p.a_stage_bytes;
-            }
-            const int row_off = p.halo ? (p.shift[nt][slot] - p.min_shift[nt]) : 0;
-            const uint32_t a_hi = a_stage + (uint32_t)row_off * 128u;
-            const uint32_t a_lo = a_hi + (uint32_t)p.a_plane_bytes;
+            const uint32_t a_tap = a_stage + (uint32_t)(p.shift[nt][slot] - p.min_shift[nt]) * 128u;
             for (int wp = 0; wp < planes; ++wp) {
               ptx::mbar_wait(b_full(sb), pb, p.err_flag, 5);
               ptx::tc_fence_after();
               const uint32_t b_addr = b_base + sb * p.b_stage_bytes;
-              for (int k = 0; k < ksteps; ++k) {
-                const uint64_t bd = make_smem_desc(b_addr + k * 32, 0);
-                ptx::umma_f16(tmem_d, make_smem_desc(a_hi + k * 32, p.desc_mode), bd, idesc, accumulate);
-                accumulate = 1;
-                if (planes == 2 && wp == 0) ptx::umma_f16(tmem_d, make_smem_desc(a_lo + k * 32, p.desc_mode), bd, idesc, 1);
+              const uint32_t first = (cb == 0 && slot == 0 && wp == 0) ? 1u : 0u;
+              for (int mbi = 0; mbi < p.mb; ++mbi) {
+                const uint32_t tmem_d = tmem_acc + (uint32_t)(mbi * p.col_stride);
+                const uint32_t a_hi = a_tap + (uint32_t)mbi * (UM_BM * 128u);
+                const uint32_t a_lo = a_hi + (uint32_t)p.a_plane_bytes;
+                for (int k = 0; k < ksteps; ++k) {
+                  const uint64_t bd = make_smem_desc(b_addr + k * 32);
+                  ptx::umma_f16(tmem_d, make_smem_desc(a_hi + k * 32), bd, idesc, (first && k == 0) ? 0u : 1u);
+                  if (planes == 2 && wp == 0) ptx::umma_f16(tmem_d, make_smem_desc(a_lo + k * 32), bd, idesc, 1u);
+                }
               }
               ptx::umma_commit(b_empty(sb));  // frees this weight stage when its MMAs retire
               if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
             }
-            if (!p.halo || slot == ntaps - 1) {
-              ptx::umma_commit(a_empty(sa));
-              if (++sa == UM_A_STAGES) { sa = 0; pa ^= 1; }
-            }
           }
+          ptx::umma_commit(a_empty(sa));
+          if (++sa == UM_A_STAGES) { sa = 0; pa ^= 1; }
         }
-        ptx::umma_commit(t_full(as));  // accumulator complete -> epilogue
-        if (++as == 2) { as = 0; ap ^= 1; }
+        ptx::umma_commit(t_full(as));  // accumulators complete -> epilogue
+        if (++as == p.t_stages) { as = 0; ap ^= 1; }
       }
     }
   } else if (warp >= 4) {
     // ================================ epilogue ====================================
-    const int q = warp - 4;  // TMEM lane quarter == warp id % 4
+    // Warp e owns TMEM lane quarter q = e % 4 (rows 32q..32q+31 of every M block) and every second
+    // (M block, 16-column chunk) work item.  Each chunk goes TMEM -> registers (thread = row) ->
+    // swizzled shared staging -> registers (4 lanes per row, 4 columns each), so that all global
+    // traffic (residual, running sum, output) is made of whole 32-byte sectors per row.
+    const int e = warp - 4;
+    const int q = e & 3;
+    const int grp = e >> 2;
+    const uint32_t stg = stg_base + (uint32_t)e * 2048u;
+    const int n_chunks = p.n_tile >> 4;
+    const int n_items = p.mb * n_chunks;
+    const int rrow = lane >> 2;   // row within an 8-row group after the transposition
+    const int g = lane & 3;       // 16-byte granule (4 columns) within the 16-column chunk
     int as = 0, ap = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int nt = (int)(tile % p.n_tiles);
       const long long mt = tile / p.n_tiles;
       const int b = (int)(mt / p.m_tiles_per_item);
-      const int t = (int)(mt % p.m_tiles_per_item) * UM_BM + q * 32 + lane;
-      const bool row_ok = t < p.L;
-      const long long row = (long long)b * p.L + t;
+      const int t0 = (int)(mt % p.m_tiles_per_item) * p.tile_rows;
       ptx::mbar_wait(t_full(as), ap, p.err_flag, 6);
       ptx::tc_fence_after();
-      const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
-      for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld32(tmem_row + (uint32_t)c0, r);
+      const uint32_t tmem_q = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * stage_cols);
+      for (int it = grp; it < n_items; it += 2) {
+        const int mbi = it / n_chunks;
+        const int c0 = (it - mbi * n_chunks) << 4;
+        const int tbase = t0 + mbi * UM_BM + q * 32;
+        if (tbase >= p.L) continue;  // whole 32-row slab past the end of the sequence (warp-uniform)
+        uint32_t r[16];
+        ptx::tmem_ld16(tmem_q + (uint32_t)(mbi * p.col_stride + c0), r);
         ptx::tmem_ld_wait();
-        if (row_ok) {
-          const int nbase = nt * p.n_tile + c0;
-          if (p.vec_ok) {
+        // stage: thread = row `lane`; granule gg of row r lives at r*64 + ((gg ^ ((r >> 1) & 3)) * 16)
+        const uint32_t wsw = (uint32_t)((lane >> 1) & 3);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (c0 + j < p.n_tile && nbase + j < p.N) {
-                float v[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])};
-                epilogue4(p.epi, row, nbase + j, v);
+        for (int gg = 0; gg < 4; ++gg) {
+          const uint32_t addr = stg + (uint32_t)lane * 64u + (((uint32_t)gg ^ wsw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r[4 * gg]), "r"(r[4 * gg + 1]), "r"(r[4 * gg + 2]), "r"(r[4 * gg + 3]) : "memory");
+        }
+        __syncwarp();
+        const int n0 = nt * p.n_tile + c0 + 4 * g;
+        const bool col_ok = n0 < p.N;
+        float v[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = rrow + 8 * i;
+          const uint32_t addr = stg + (uint32_t)rr * 64u + (((uint32_t)g ^ (uint32_t)((rr >> 1) & 3)) << 4);
+          uint32_t a0, a1, a2, a3;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(addr) : "memory");
+          v[i][0] = __uint_as_float(a0); v[i][1] = __uint_as_float(a1); v[i][2] = __uint_as_float(a2); v[i][3] = __uint_as_float(a3);
+        }
+        __syncwarp();
+        if (col_ok) {
+          if (p.vec_ok) {
+            // all loads of the chunk first (out may alias res: in-place residual update), then math + stores
+            float rs[4][4], ac[4][4];
+            const float4 bias = *reinterpret_cast<const float4*>(p.epi.bias + n0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int t = tbase + rrow + 8 * i;
+              const long long off = ((long long)b * p.L + t) * p.epi.N + n0;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) rs[i][j] = ac[i][j] = 0.f;
+              if (t < p.L) {
+                if (p.epi.res) epi_load4(p.epi.res, p.epi.res_dtype, off, rs[i]);
+                if (p.epi.acc) epi_load4(p.epi.acc, p.epi.acc_dtype, off, ac[i]);
               }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int t = tbase + rrow + 8 * i;
+              if (t >= p.L) continue;
+              const long long off = ((long long)b * p.L + t) * p.epi.N + n0;
+              v[i][0] += bias.x; v[i][1] += bias.y; v[i][2] += bias.z; v[i][3] += bias.w;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                v[i][j] = (v[i][j] + rs[i][j]) + ac[i][j];
+                if (p.epi.use_div) v[i][j] = __fdiv_rn(v[i][j], p.epi.div);
+              }
+              epi_store4(p.epi, off, v[i]);
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c0 + j < p.n_tile && nbase + j < p.N) epilogue1(p.epi, row, nbase + j, __uint_as_float(r[j]));
+            for (int i = 0; i < 4; ++i) {
+              const int t = tbase + rrow + 8 * i;
+              if (t >= p.L) continue;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (n0 + j < p.N) epilogue1(p.epi, (long long)b * p.L + t, n0 + j, v[i][j]);
+            }
           }
         }
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(t_empty(as));
-      if (++as == 2) { as = 0; ap ^= 1; }
+      if (++as == p.t_stages) { as = 0; ap ^= 1; }
     }
   }
 
@@ -399,8 +475,8 @@ static int encode_bf16_map(CUtensorMap* map, void* base, int rank, const cuuint6
   return BVG_OK;
 }
 
-int umma_a_mode = 1;     // tuning/test hook: 1 = HALO boxes, 0 = one box per tap
-int umma_desc_mode = 0;  // tuning/test hook: base_offset policy for row-shifted descriptors
+int umma_mb = 0;         // tuning/test hook: force M blocks per tile (0 = choose)
+int umma_wide_mb2 = 0;   // tuning/test hook: allow mb = 2 with a single TMEM stage for 256-column tiles
 int umma_max_ctas = 0;   // tuning/test hook: cap the persistent grid
 
 struct UmmaLaunch {
@@ -408,6 +484,22 @@ struct UmmaLaunch {
   int grid;
   size_t smem;
 };
+
+static const int kBarBytes = 8 * (2 * UM_A_STAGES + 2 * UM_MAX_B_STAGES + 2 * UM_MAX_T_STAGES) + 16;
+
+// shared-memory plan for a given number of M blocks; returns the number of weight stages that fit
+static int plan_smem(int mb, int max_span, int planes, int n_tile, int* box_rows, int* boxes) {
+  const int rows = mb * UM_BM + max_span;
+  const int nb = (rows + 255) / 256;
+  const int br = (((rows + nb - 1) / nb) + 7) / 8 * 8;
+  *box_rows = br;
+  *boxes = nb;
+  const int a_stage = nb * br * 128 * planes;
+  const int avail = UM_SMEM_LIMIT - 1024 - kBarBytes - UM_STAGING_BYTES - UM_A_STAGES * a_stage;
+  if (avail <= 0) return 0;
+  int bs = avail / (n_tile * 128);
+  return bs > UM_MAX_B_STAGES ? UM_MAX_B_STAGES : bs;
+}
 
 int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out) {
   const bvg_conv_weights* w = d->w;
@@ -435,10 +527,7 @@ int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out) {
   p.tap_stride = w->tap_stride;
   p.n_cb = w->cin_pad / UM_KB;
   p.cin = w->cin;
-  p.m_tiles_per_item = ceil_div(d->L, UM_BM);
-  p.total_tiles = (long long)d->B * p.m_tiles_per_item * w->n_tiles;
   p.vec_ok = (w->n_total % 4 == 0) ? 1 : 0;
-  p.desc_mode = umma_desc_mode;
   int max_span = 0;
   for (int t = 0; t < w->n_tiles; ++t) {
     BVG_REQUIRE(w->n_taps[t] > 0 && w->n_taps[t] <= BVG_MAX_TAPS, "conv_umma: bad tap count");
@@ -452,20 +541,45 @@ int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out) {
     p.min_shift[t] = lo;
     if (hi - lo > max_span) max_span = hi - lo;
   }
-  p.halo = (umma_a_mode != 0 && UM_BM + max_span <= 256) ? 1 : 0;
-  p.a_rows = p.halo ? ((UM_BM + max_span + 7) / 8) * 8 : UM_BM;
-  p.a_plane_bytes = p.a_rows * 128;
+
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+
+  // M blocks per tile: every weight box is then reused by mb MMAs and the per-tile pipeline
+  // latencies (TMA round trip, accumulator hand-over, epilogue) are paid once per mb*128 rows.
+  // Constraints: >= 2 accumulator stages in the 512 TMEM columns, >= 3 weight stages in shared
+  // memory next to two A super-tiles, and enough tiles to fill the machine twice.
+  p.col_stride = (w->n_tile + 31) / 32 * 32;
+  int mb = 1;
+  for (int cand = UM_MAX_MB; cand >= 1; cand >>= 1) {
+    int br, nb;
+    const bool tmem_ok = cand * p.col_stride * 2 <= 512 || (cand == 1) || (umma_wide_mb2 && cand == 2 && cand * p.col_stride <= 512);
+    if (!tmem_ok) continue;
+    if (plan_smem(cand, max_span, planes, w->n_tile, &br, &nb) < (cand == 1 ? 2 : 3)) continue;
+    const long long tiles = (long long)d->B * ceil_div(d->L, cand * UM_BM) * w->n_tiles;
+    if (cand > 1 && tiles < 2ll * sms) continue;
+    mb = cand;
+    break;
+  }
+  if (umma_mb > 0) mb = umma_mb;
+  BVG_REQUIRE(mb >= 1 && mb <= UM_MAX_MB && mb * p.col_stride <= 512, "conv_umma: bad M-block count %d for n_tile %d", mb, w->n_tile);
+  p.mb = mb;
+  p.tile_rows = mb * UM_BM;
+  p.m_tiles_per_item = ceil_div(d->L, p.tile_rows);
+  p.total_tiles = (long long)d->B * p.m_tiles_per_item * w->n_tiles;
+  p.t_stages = 512 / (mb * p.col_stride);
+  if (p.t_stages > UM_MAX_T_STAGES) p.t_stages = UM_MAX_T_STAGES;
+  const int bs = plan_smem(mb, max_span, planes, w->n_tile, &p.a_box_rows, &p.a_boxes);
+  BVG_REQUIRE(bs >= 2, "conv_umma: tile does not fit in shared memory (mb %d, span %d, n_tile %d, planes %d)", mb, max_span, w->n_tile, planes);
+  p.b_stages = bs;
+  p.a_plane_bytes = p.a_boxes * p.a_box_rows * 128;
   p.a_stage_bytes = p.a_plane_bytes * planes;
   p.b_stage_bytes = w->n_tile * 128;
-  const int bar_bytes = 8 * (2 * UM_A_STAGES + 2 * UM_MAX_B_STAGES + 4) + 16;
-  const int avail = UM_SMEM_LIMIT - 1024 /*alignment slack*/ - bar_bytes - UM_A_STAGES * p.a_stage_bytes;
-  int bs = avail / p.b_stage_bytes;
-  if (bs > UM_MAX_B_STAGES) bs = UM_MAX_B_STAGES;
-  BVG_REQUIRE(bs >= 2, "conv_umma: tile does not fit in shared memory (a_rows %d, n_tile %d)", p.a_rows, w->n_tile);
-  p.b_stages = bs;
-  size_t smem = 1024 + (size_t)UM_A_STAGES * p.a_stage_bytes + (size_t)bs * p.b_stage_bytes + bar_bytes;
+  size_t smem = 1024 + (size_t)UM_A_STAGES * p.a_stage_bytes + (size_t)bs * p.b_stage_bytes + UM_STAGING_BYTES + kBarBytes;
   // keep one CTA per SM (each allocates all 512 TMEM columns): ask for more than half the SM's smem
   if (smem < 120 * 1024) smem = 120 * 1024;
+  BVG_REQUIRE(smem <= (size_t)UM_SMEM_LIMIT, "conv_umma: shared memory plan exceeds the limit");
   out->smem = smem;
 
   // tensor maps
@@ -473,7 +587,7 @@ int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out) {
     void* xb = pl == 0 ? d->x.d_ptr : d->x.d_lo;
     cuuint64_t dims[3] = {(cuuint64_t)w->x_pitch, (cuuint64_t)d->L, (cuuint64_t)d->B};
     cuuint64_t strides[2] = {(cuuint64_t)w->x_pitch * 2, (cuuint64_t)w->x_pitch * 2 * (cuuint64_t)d->L};
-    cuuint32_t box[3] = {(cuuint32_t)UM_KB, (cuuint32_t)p.a_rows, 1};
+    cuuint32_t box[3] = {(cuuint32_t)UM_KB, (cuuint32_t)p.a_box_rows, 1};
     rc = encode_bf16_map(&p.tm_x[pl], xb, 3, dims, strides, box, "activation");
     if (rc != BVG_OK) return rc;
     void* wb = pl == 0 ? w->d_w : w->d_w_lo;
@@ -484,9 +598,6 @@ int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out) {
     if (rc != BVG_OK) return rc;
   }
 
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   long long grid = p.total_tiles < sms ? p.total_tiles : sms;
   if (umma_max_ctas > 0 && grid > umma_max_ctas) grid = umma_max_ctas;
   out->grid = (int)grid;

@@ -43,6 +43,21 @@ __device__ __forceinline__ void epi_store_bf16x4(void* base, long long off, cons
   *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(base) + off) = t;
 }
 
+// store 4 finished values at element offset `off` in the output format
+__device__ __forceinline__ void epi_store4(const EpiParams& e, long long off, const float (&v)[4]) {
+  if (e.out_dtype == BVG_F32) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + off) = make_float4(v[0], v[1], v[2], v[3]);
+  } else if (e.out_dtype == BVG_BF16) {
+    epi_store_bf16x4(e.out, off, v);
+  } else {
+    float hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_bf16(v[i], hi[i], lo[i]);
+    epi_store_bf16x4(e.out, off, hi);
+    epi_store_bf16x4(e.out_lo, off, lo);
+  }
+}
+
 // 4 consecutive outputs n0..n0+3 of one row; requires N % 4 == 0 and n0 % 4 == 0.
 __device__ __forceinline__ void epilogue4(const EpiParams& e, long long row, int n0, float (&v)[4]) {
   const long long off = row * e.N + n0;

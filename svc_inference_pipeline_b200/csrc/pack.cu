@@ -101,6 +101,8 @@ __global__ void pack_bias_kernel(const float* __restrict__ bias, int cout, int n
   out[n] = (n < n_total && bias != nullptr) ? bias[n % cout] : 0.f;
 }
 
+int umma_ntile_cap = 256;  // tuning hook: widest UMMA N tile chosen by conv_geometry (multiple of 16)
+
 static int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
@@ -130,10 +132,11 @@ int conv_geometry(const bvg_conv_geom* g, bvg_conv_weights* w) {
     } else {
       // fewest tiles of at most 256 columns; a transposed conv keeps each tile inside one phase
       // when the per-phase width allows (then every tile has exactly the taps of its phase)
+      const int cap = (umma_ntile_cap >= 16 && umma_ntile_cap <= 256) ? umma_ntile_cap / 16 * 16 : 256;
       const int base = (tr && g->cout % 16 == 0) ? g->cout : n_total;
-      const int t = ceil_div(base, 256);
+      const int t = ceil_div(base, cap);
       n_tile = round_up(ceil_div(base, t), 16);
-      if (tr && g->cout % 16 == 0 && g->cout % n_tile != 0) n_tile = round_up(ceil_div(n_total, ceil_div(n_total, 256)), 16);
+      if (tr && g->cout % 16 == 0 && g->cout % n_tile != 0) n_tile = round_up(ceil_div(n_total, ceil_div(n_total, cap)), 16);
     }
     BVG_REQUIRE(n_tile % 16 == 0 && n_tile >= 16 && n_tile <= 256, "conv geometry: UMMA n_tile %d must be a multiple of 16 in [16, 256]", n_tile);
   }

@@ -200,21 +200,21 @@ UMMA_CONV_CASES = [
 ]
 
 
-def _umma_conv_check(ops, B, Ch, Ln, k, d, split, a_mode, desc_mode):
+def _umma_conv_check(ops, B, Ch, Ln, k, d, split, mb):
     _ops, L = ops
     rng = np.random.default_rng(100 + Ch + k + d)
     x = rng.standard_normal((B, Ch, Ln)).astype(np.float32)
     v = (rng.standard_normal((Ch, Ch, k)) / np.sqrt(Ch * k)).astype(np.float32)
     g = (np.sqrt((v.astype(np.float64) ** 2).sum(axis=(1, 2), keepdims=True)) * rng.uniform(0.7, 1.4, (Ch, 1, 1))).astype(np.float32)
     b = (rng.standard_normal(Ch) * 0.1).astype(np.float32)
-    L.set_tuning("umma_a_mode", a_mode)
-    L.set_tuning("umma_desc_mode", desc_mode)
+    L.set_tuning("umma_mb", mb)
     try:
         pc = _ops.pack_conv(*(torch.from_numpy(t).to(DEV) for t in (v, g, b)), dilation=d, padding=O.get_padding(k, d), backend=L.UMMA, split=split)
+        if mb * ((pc.desc.n_tile + 31) // 32 * 32) > 512:
+            pytest.skip("accumulators of this many M blocks do not fit in TMEM")
         y = cf(_ops.conv(cl(x), pc))
     finally:
-        L.set_tuning("umma_a_mode", 1)
-        L.set_tuning("umma_desc_mode", 0)
+        L.set_tuning("umma_mb", 0)
     ref, w = _oracle_conv(x, v, g, b, False, k, d=d)
     if split:
         err = np.abs(y - ref).max()
@@ -229,20 +229,23 @@ def _umma_conv_check(ops, B, Ch, Ln, k, d, split, a_mode, desc_mode):
 
 
 @pytest.mark.parametrize("case", UMMA_CONV_CASES)
-def test_conv_umma_per_tap(ops, case):
-    """A operand loaded once per tap (no descriptor row offsets): the conservative mode."""
-    _umma_conv_check(ops, *case, split=False, a_mode=0, desc_mode=0)
+@pytest.mark.parametrize("mb", [0, 1, 2, 4])
+def test_conv_umma_bf16(ops, case, mb):
+    """bf16 operands; mb = M blocks per tile (0 = the host heuristic).  Every tap reads one shared A
+    halo tile through row-shifted UMMA descriptors."""
+    _umma_conv_check(ops, *case, split=False, mb=mb)
 
 
-@pytest.mark.parametrize("case", UMMA_CONV_CASES)
-def test_conv_umma_halo(ops, case):
-    """A operand loaded once per Cin slice, taps addressed by row-shifted UMMA descriptors."""
-    _umma_conv_check(ops, *case, split=False, a_mode=1, desc_mode=0)
+@pytest.mark.parametrize("case", UMMA_CONV_CASES[:7])
+@pytest.mark.parametrize("mb", [0, 1, 2])
+def test_conv_umma_split(ops, case, mb):
+    _umma_conv_check(ops, *case, split=True, mb=mb)
 
 
-@pytest.mark.parametrize("case", UMMA_CONV_CASES[:6])
-def test_conv_umma_split(ops, case):
-    _umma_conv_check(ops, *case, split=True, a_mode=1, desc_mode=0)
+def test_conv_umma_large_rows(ops):
+    """Many tiles per CTA (pipeline wrap-around of every barrier ring) and ragged last tiles."""
+    _umma_conv_check(ops, 4, 48, 20011, 7, 3, split=False, mb=0)
+    _umma_conv_check(ops, 2, 192, 9001, 3, 1, split=True, mb=0)
 
 
 @pytest.mark.parametrize("cin,cout,k,u,Ln", [(64, 32, 8, 4, 50), (128, 64, 4, 2, 333), (48, 24, 4, 2, 200), (256, 128, 16, 8, 40), (1536, 768, 8, 4, 20)])

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-CASES = ["amp", "simt", "umma_pertap", "umma_halo0", "umma_halo1", "umma_split", "umma_convT", "tiny_gen"]
+CASES = ["amp", "simt", "umma_mb1", "umma_mb2", "umma_mb4", "umma_split", "umma_convT", "tiny_gen"]
 
 
 def run_case(name):
@@ -44,13 +44,12 @@ def run_case(name):
         g.smoke()
         return
 
-    def conv_case(B, Ch, Ln, k, d, backend, split, a_mode=1, desc_mode=0):
+    def conv_case(B, Ch, Ln, k, d, backend, split, mb=0):
         x = rng.standard_normal((B, Ch, Ln)).astype(np.float32)
         v = (rng.standard_normal((Ch, Ch, k)) / np.sqrt(Ch * k)).astype(np.float32)
         g = (np.sqrt((v.astype(np.float64) ** 2).sum(axis=(1, 2), keepdims=True)) * rng.uniform(0.7, 1.4, (Ch, 1, 1))).astype(np.float32)
         b = (rng.standard_normal(Ch) * 0.1).astype(np.float32)
-        L.set_tuning("umma_a_mode", a_mode)
-        L.set_tuning("umma_desc_mode", desc_mode)
+        L.set_tuning("umma_mb", mb)
         pc = ops.pack_conv(*(torch.from_numpy(t).to(dev) for t in (v, g, b)), dilation=d, padding=O.get_padding(k, d), backend=backend, split=split)
         y = cf(ops.conv(cl(x), pc))
         torch.cuda.synchronize()
@@ -63,25 +62,19 @@ def run_case(name):
     if name == "simt":
         for s in shapes[:3]:
             conv_case(*s, backend=L.SIMT, split=False)
-    elif name == "umma_pertap":
+    elif name in ("umma_mb1", "umma_mb2", "umma_mb4"):
         for s in shapes:
-            conv_case(*s, backend=L.UMMA, split=False, a_mode=0)
-    elif name == "umma_halo0":
-        for s in shapes:
-            conv_case(*s, backend=L.UMMA, split=False, a_mode=1, desc_mode=0)
-    elif name == "umma_halo1":
-        for s in shapes:
-            conv_case(*s, backend=L.UMMA, split=False, a_mode=1, desc_mode=1)
+            if int(name[-1]) * (256 if s[1] >= 256 else 128) <= 512:
+                conv_case(*s, backend=L.UMMA, split=False, mb=int(name[-1]))
     elif name == "umma_split":
         for s in shapes:
-            conv_case(*s, backend=L.UMMA, split=True, a_mode=0)
+            conv_case(*s, backend=L.UMMA, split=True)
     elif name == "umma_convT":
         for cin, cout, k, u, Ln in [(64, 32, 8, 4, 50), (48, 24, 4, 2, 200)]:
             x = rng.standard_normal((2, cin, Ln)).astype(np.float32)
             v = (rng.standard_normal((cin, cout, k)) / np.sqrt(cin * k / u)).astype(np.float32)
             g = np.sqrt((v.astype(np.float64) ** 2).sum(axis=(1, 2), keepdims=True)).astype(np.float32)
             b = (rng.standard_normal(cout) * 0.1).astype(np.float32)
-            L.set_tuning("umma_a_mode", 0)
             pc = ops.pack_conv(*(torch.from_numpy(t).to(dev) for t in (v, g, b)), transposed=True, stride=u, padding=(k - u) // 2, backend=L.UMMA, split=False)
             y = cf(ops.conv(cl(x), pc).reshape(2, Ln * u, cout))
             w = O.weight_norm_fold(v.astype(np.float64), g.astype(np.float64))
