@@ -289,12 +289,19 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
+    // One thread feeds the tensor pipe, so its instruction count per MMA is the budget that
+    // matters (a lone warp issues one dependent instruction every few cycles): descriptors are
+    // kept as a constant high word plus a low word that only needs integer adds.
     if (lane == 0) {
       const uint32_t idesc = make_idesc(p.n_tile);
+      const uint64_t desc_hi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;  // SBO, version, SWIZZLE_128B
+      const uint32_t a_plane16 = (uint32_t)p.a_plane_bytes >> 4;
+      const bool split = p.planes == 2;
       int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, ap = 0;
       for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int nt = (int)(tile % p.n_tiles);
         const int ntaps = p.n_taps[nt];
+        const int min_shift = p.min_shift[nt];
         ptx::mbar_wait(t_empty(as), ap ^ 1, p.err_flag, 3);
         ptx::tc_fence_after();
         const uint32_t tmem_acc = tmem_base + (uint32_t)(as * stage_cols);
@@ -302,23 +309,28 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
           const int valid = min(UM_KB, p.cin - cb * UM_KB);
           const int ksteps = (valid + 15) >> 4;
           ptx::mbar_wait(a_full(sa), pa, p.err_flag, 4);
-          const uint32_t a_stage = a_base + sa * p.a_stage_bytes;
+          const uint32_t a_stage16 = (((a_base + sa * p.a_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
           for (int slot = 0; slot < ntaps; ++slot) {
-            const uint32_t a_tap = a_stage + (uint32_t)(p.shift[nt][slot] - p.min_shift[nt]) * 128u;
+            const uint32_t a_tap16 = a_stage16 + (uint32_t)(p.shift[nt][slot] - min_shift) * 8u;  // 128 B per row
             for (int wp = 0; wp < planes; ++wp) {
               ptx::mbar_wait(b_full(sb), pb, p.err_flag, 5);
               ptx::tc_fence_after();
-              const uint32_t b_addr = b_base + sb * p.b_stage_bytes;
-              const uint32_t first = (cb == 0 && slot == 0 && wp == 0) ? 1u : 0u;
+              const uint32_t b16 = (((b_base + sb * p.b_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+              const uint32_t first = (cb == 0 && slot == 0 && wp == 0) ? 0u : 1u;  // 0 => overwrite the accumulator
+              const bool with_lo = split && wp == 0;
+              uint32_t a16 = a_tap16;
+              uint32_t tmem_d = tmem_acc;
               for (int mbi = 0; mbi < p.mb; ++mbi) {
-                const uint32_t tmem_d = tmem_acc + (uint32_t)(mbi * p.col_stride);
-                const uint32_t a_hi = a_tap + (uint32_t)mbi * (UM_BM * 128u);
-                const uint32_t a_lo = a_hi + (uint32_t)p.a_plane_bytes;
-                for (int k = 0; k < ksteps; ++k) {
-                  const uint64_t bd = make_smem_desc(b_addr + k * 32);
-                  ptx::umma_f16(tmem_d, make_smem_desc(a_hi + k * 32), bd, idesc, (first && k == 0) ? 0u : 1u);
-                  if (planes == 2 && wp == 0) ptx::umma_f16(tmem_d, make_smem_desc(a_lo + k * 32), bd, idesc, 1u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if (k < ksteps) {
+                    const uint64_t bd = desc_hi | (uint64_t)(b16 + 2u * k);
+                    ptx::umma_f16(tmem_d, desc_hi | (uint64_t)(a16 + 2u * k), bd, idesc, k == 0 ? first : 1u);
+                    if (with_lo) ptx::umma_f16(tmem_d, desc_hi | (uint64_t)(a16 + a_plane16 + 2u * k), bd, idesc, 1u);
+                  }
                 }
+                a16 += (UM_BM * 128u) >> 4;
+                tmem_d += (uint32_t)p.col_stride;
               }
               ptx::umma_commit(b_empty(sb));  // frees this weight stage when its MMAs retire
               if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
@@ -345,71 +357,108 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
     const int n_items = p.mb * n_chunks;
     const int rrow = lane >> 2;   // row within an 8-row group after the transposition
     const int g = lane & 3;       // 16-byte granule (4 columns) within the 16-column chunk
+    const int n_my = (n_items - grp + 1) >> 1;  // items grp, grp+2, ...
+    const bool res_f32 = p.epi.res_dtype == BVG_F32;
     int as = 0, ap = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int nt = (int)(tile % p.n_tiles);
       const long long mt = tile / p.n_tiles;
       const int b = (int)(mt / p.m_tiles_per_item);
       const int t0 = (int)(mt % p.m_tiles_per_item) * p.tile_rows;
-      ptx::mbar_wait(t_full(as), ap, p.err_flag, 6);
-      ptx::tc_fence_after();
+      const long long row_base = (long long)b * p.L;
       const uint32_t tmem_q = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * stage_cols);
-      for (int it = grp; it < n_items; it += 2) {
-        const int mbi = it / n_chunks;
-        const int c0 = (it - mbi * n_chunks) << 4;
-        const int tbase = t0 + mbi * UM_BM + q * 32;
-        if (tbase >= p.L) continue;  // whole 32-row slab past the end of the sequence (warp-uniform)
-        uint32_t r[16];
-        ptx::tmem_ld16(tmem_q + (uint32_t)(mbi * p.col_stride + c0), r);
-        ptx::tmem_ld_wait();
-        // stage: thread = row `lane`; granule gg of row r lives at r*64 + ((gg ^ ((r >> 1) & 3)) * 16)
-        const uint32_t wsw = (uint32_t)((lane >> 1) & 3);
+      // items are handled two at a time: the residual of both is requested before anything waits
+      // (for the first pair: before the accumulator is even complete), so that the loads of a
+      // whole pair -- 8 per lane -- are in flight together instead of one latency per chunk
+      for (int pb2 = 0; pb2 < n_my; pb2 += 2) {
+        uint4 raw[2][4];
+        int it_mbi[2], it_c0[2];
 #pragma unroll
-        for (int gg = 0; gg < 4; ++gg) {
-          const uint32_t addr = stg + (uint32_t)lane * 64u + (((uint32_t)gg ^ wsw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r[4 * gg]), "r"(r[4 * gg + 1]), "r"(r[4 * gg + 2]), "r"(r[4 * gg + 3]) : "memory");
-        }
-        __syncwarp();
-        const int n0 = nt * p.n_tile + c0 + 4 * g;
-        const bool col_ok = n0 < p.N;
-        float v[4][4];
+        for (int u = 0; u < 2; ++u) {
+          const int it = grp + 2 * (pb2 + u);
+          const int mbi = it / n_chunks;
+          it_mbi[u] = mbi;
+          it_c0[u] = (it - mbi * n_chunks) << 4;
+          const int tbase = t0 + mbi * UM_BM + q * 32;
+          const int n0 = nt * p.n_tile + it_c0[u] + 4 * g;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int rr = rrow + 8 * i;
-          const uint32_t addr = stg + (uint32_t)rr * 64u + (((uint32_t)g ^ (uint32_t)((rr >> 1) & 3)) << 4);
-          uint32_t a0, a1, a2, a3;
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(addr) : "memory");
-          v[i][0] = __uint_as_float(a0); v[i][1] = __uint_as_float(a1); v[i][2] = __uint_as_float(a2); v[i][3] = __uint_as_float(a3);
+          for (int i = 0; i < 4; ++i) {
+            raw[u][i] = make_uint4(0u, 0u, 0u, 0u);
+            const int t = tbase + rrow + 8 * i;
+            if (p.epi.res && p.vec_ok && pb2 + u < n_my && t < p.L && n0 < p.N) {
+              const long long off = (row_base + t) * p.epi.N + n0;
+              if (res_f32) {
+                raw[u][i] = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.epi.res) + off);
+              } else {
+                const uint2 h = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.epi.res) + off);
+                raw[u][i].x = h.x;
+                raw[u][i].y = h.y;
+              }
+            }
+          }
         }
-        __syncwarp();
-        if (col_ok) {
+        if (pb2 == 0) {
+          ptx::mbar_wait(t_full(as), ap, p.err_flag, 6);
+          ptx::tc_fence_after();
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (pb2 + u >= n_my) continue;
+          const int mbi = it_mbi[u], c0 = it_c0[u];
+          const int tbase = t0 + mbi * UM_BM + q * 32;
+          if (tbase >= p.L) continue;  // whole 32-row slab past the end of the sequence (warp-uniform)
+          uint32_t r[16];
+          ptx::tmem_ld16(tmem_q + (uint32_t)(mbi * p.col_stride + c0), r);
+          ptx::tmem_ld_wait();
+          // stage: thread = row `lane`; granule gg of row r lives at r*64 + ((gg ^ ((r >> 1) & 3)) * 16)
+          const uint32_t wsw = (uint32_t)((lane >> 1) & 3);
+#pragma unroll
+          for (int gg = 0; gg < 4; ++gg) {
+            const uint32_t addr = stg + (uint32_t)lane * 64u + (((uint32_t)gg ^ wsw) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r[4 * gg]), "r"(r[4 * gg + 1]), "r"(r[4 * gg + 2]), "r"(r[4 * gg + 3]) : "memory");
+          }
+          __syncwarp();
+          const int n0 = nt * p.n_tile + c0 + 4 * g;
+          float v[4][4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = rrow + 8 * i;
+            const uint32_t addr = stg + (uint32_t)rr * 64u + (((uint32_t)g ^ (uint32_t)((rr >> 1) & 3)) << 4);
+            uint32_t a0, a1, a2, a3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(addr) : "memory");
+            v[i][0] = __uint_as_float(a0); v[i][1] = __uint_as_float(a1); v[i][2] = __uint_as_float(a2); v[i][3] = __uint_as_float(a3);
+          }
+          __syncwarp();
+          if (n0 >= p.N) continue;
           if (p.vec_ok) {
-            // all loads of the chunk first (out may alias res: in-place residual update), then math + stores
-            float rs[4][4], ac[4][4];
             const float4 bias = *reinterpret_cast<const float4*>(p.epi.bias + n0);
+            float ac[4][4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int t = tbase + rrow + 8 * i;
-              const long long off = ((long long)b * p.L + t) * p.epi.N + n0;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) rs[i][j] = ac[i][j] = 0.f;
-              if (t < p.L) {
-                if (p.epi.res) epi_load4(p.epi.res, p.epi.res_dtype, off, rs[i]);
-                if (p.epi.acc) epi_load4(p.epi.acc, p.epi.acc_dtype, off, ac[i]);
-              }
+              for (int j = 0; j < 4; ++j) ac[i][j] = 0.f;
+              if (p.epi.acc && t < p.L) epi_load4(p.epi.acc, p.epi.acc_dtype, (row_base + t) * p.epi.N + n0, ac[i]);
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int t = tbase + rrow + 8 * i;
               if (t >= p.L) continue;
-              const long long off = ((long long)b * p.L + t) * p.epi.N + n0;
+              float rs[4];
+              if (res_f32) {
+                rs[0] = __uint_as_float(raw[u][i].x); rs[1] = __uint_as_float(raw[u][i].y);
+                rs[2] = __uint_as_float(raw[u][i].z); rs[3] = __uint_as_float(raw[u][i].w);
+              } else {
+                unpack_bf16x2(raw[u][i].x, rs[0], rs[1]);
+                unpack_bf16x2(raw[u][i].y, rs[2], rs[3]);
+              }
               v[i][0] += bias.x; v[i][1] += bias.y; v[i][2] += bias.z; v[i][3] += bias.w;
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                v[i][j] = (v[i][j] + rs[i][j]) + ac[i][j];
+                v[i][j] = (v[i][j] + rs[j]) + ac[i][j];
                 if (p.epi.use_div) v[i][j] = __fdiv_rn(v[i][j], p.epi.div);
               }
-              epi_store4(p.epi, off, v[i]);
+              epi_store4(p.epi, (row_base + t) * p.epi.N + n0, v[i]);
             }
           } else {
 #pragma unroll
@@ -418,10 +467,14 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
               if (t >= p.L) continue;
 #pragma unroll
               for (int j = 0; j < 4; ++j)
-                if (n0 + j < p.N) epilogue1(p.epi, (long long)b * p.L + t, n0 + j, v[i][j]);
+                if (n0 + j < p.N) epilogue1(p.epi, row_base + t, n0 + j, v[i][j]);
             }
           }
         }
+      }
+      if (n_my == 0) {
+        ptx::mbar_wait(t_full(as), ap, p.err_flag, 6);
+        ptx::tc_fence_after();
       }
       ptx::tc_fence_before();
       __syncwarp();

@@ -13,7 +13,12 @@ ap.add_argument("--precision", default="fp32")
 ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--frames", type=int, default=938)
 ap.add_argument("--out", default=None)
+ap.add_argument("--tune", action="append", default=[], help="name=value tuning knob (bvg_set_tuning)")
 a = ap.parse_args()
+from svc_inference_pipeline_b200 import _lib as _L
+for kv in a.tune:
+    k, v = kv.split("=")
+    _L.set_tuning(k, int(v))
 cfg = load_config(os.path.join(ROOT, "svc_inference_pipeline_b200", "config", "config.json"))
 m = Generator(cfg.vocoder, precision=a.precision)
 m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.synthetic_state_dict({k: cfg.vocoder[k] for k in cfg.vocoder.keys()}, 0).items()})
@@ -23,7 +28,7 @@ for _ in range(2):
     m(mel)
 rows = m.profile_ops(a.batch, a.frames, reps=2)
 tot = sum(r[2] for r in rows)
-lines = [f"# precision={a.precision} batch={a.batch} frames={a.frames} total={tot:.2f} ms"]
+lines = [f"# precision={a.precision} batch={a.batch} frames={a.frames} tune={a.tune} total={tot:.2f} ms"]
 agg = {}
 for lab, kind, ms, work in rows:
     rate = (work / (ms * 1e-3) / 1e12 if kind == "conv" else work / (ms * 1e-3) / 1e9) if ms > 0 else 0
