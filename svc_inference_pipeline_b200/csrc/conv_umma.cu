@@ -74,6 +74,17 @@ namespace ptx {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one elected lane of a fully converged warp (CUTLASS' elect_one_sync)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -215,7 +226,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));  // generic pointer to smem_base
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -256,7 +267,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    // The whole warp runs the loop convergently (all operands stay in uniform registers); only
+    // the TMA / mbarrier instructions themselves are predicated on one elected lane.
+    {
       int sa = 0, pa = 0, sb = 0, pb = 0;
       const int box_bytes = p.a_box_rows * 128;
       for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -269,18 +282,24 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
         for (int cb = 0; cb < p.n_cb; ++cb) {
           // A super-tile: rows [row0, row0 + a_boxes * a_box_rows) x 64 channels, every plane
           ptx::mbar_wait(a_empty(sa), pa ^ 1, p.err_flag, 1);
-          ptx::mbar_expect_tx(a_full(sa), (uint32_t)p.a_stage_bytes);
-          for (int pl = 0; pl < planes; ++pl)
-            for (int bx = 0; bx < p.a_boxes; ++bx)
-              ptx::tma_load_3d(a_base + sa * p.a_stage_bytes + pl * p.a_plane_bytes + bx * box_bytes, &p.tm_x[pl], a_full(sa), cb * UM_KB,
-                               row0 + bx * p.a_box_rows, b);
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(a_full(sa), (uint32_t)p.a_stage_bytes);
+            for (int pl = 0; pl < planes; ++pl)
+              for (int bx = 0; bx < p.a_boxes; ++bx)
+                ptx::tma_load_3d(a_base + sa * p.a_stage_bytes + pl * p.a_plane_bytes + bx * box_bytes, &p.tm_x[pl], a_full(sa), cb * UM_KB,
+                                 row0 + bx * p.a_box_rows, b);
+          }
+          __syncwarp();
           if (++sa == UM_A_STAGES) { sa = 0; pa ^= 1; }
           for (int slot = 0; slot < ntaps; ++slot) {
             for (int wp = 0; wp < planes; ++wp) {
               ptx::mbar_wait(b_empty(sb), pb ^ 1, p.err_flag, 2);
-              ptx::mbar_expect_tx(b_full(sb), (uint32_t)p.b_stage_bytes);
-              ptx::tma_load_2d(b_base + sb * p.b_stage_bytes, &p.tm_w[wp], b_full(sb), cb * UM_KB,
-                               (nt * p.tap_stride + slot) * p.n_tile);
+              if (ptx::elect_one()) {
+                ptx::mbar_expect_tx(b_full(sb), (uint32_t)p.b_stage_bytes);
+                ptx::tma_load_2d(b_base + sb * p.b_stage_bytes, &p.tm_w[wp], b_full(sb), cb * UM_KB,
+                                 (nt * p.tap_stride + slot) * p.n_tile);
+              }
+              __syncwarp();
               if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
             }
           }
@@ -291,8 +310,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
     // ================================ MMA issuer ==================================
     // One thread feeds the tensor pipe, so its instruction count per MMA is the budget that
     // matters (a lone warp issues one dependent instruction every few cycles): descriptors are
-    // kept as a constant high word plus a low word that only needs integer adds.
-    if (lane == 0) {
+    // kept as a constant high word plus a low word that only needs integer adds, and the warp
+    // stays converged so that every tcgen05 operand lives in a uniform register -- issuing from
+    // inside an `if (lane == 0)` region makes the compiler wrap each UTCHMMA in an
+    // ELECT / R2UR.BROADCAST "waterfall" loop (~15 instructions per MMA, measured 2-10x slower).
+    {
       const uint32_t idesc = make_idesc(p.n_tile);
       const uint64_t desc_hi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;  // SBO, version, SWIZZLE_128B
       const uint32_t a_plane16 = (uint32_t)p.a_plane_bytes >> 4;
@@ -325,21 +347,24 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
                 for (int k = 0; k < 4; ++k) {
                   if (k < ksteps) {
                     const uint64_t bd = desc_hi | (uint64_t)(b16 + 2u * k);
-                    ptx::umma_f16(tmem_d, desc_hi | (uint64_t)(a16 + 2u * k), bd, idesc, k == 0 ? first : 1u);
-                    if (with_lo) ptx::umma_f16(tmem_d, desc_hi | (uint64_t)(a16 + a_plane16 + 2u * k), bd, idesc, 1u);
+                    if (ptx::elect_one()) ptx::umma_f16(tmem_d, desc_hi | (uint64_t)(a16 + 2u * k), bd, idesc, k == 0 ? first : 1u);
+                    if (with_lo && ptx::elect_one()) ptx::umma_f16(tmem_d, desc_hi | (uint64_t)(a16 + a_plane16 + 2u * k), bd, idesc, 1u);
                   }
                 }
                 a16 += (UM_BM * 128u) >> 4;
                 tmem_d += (uint32_t)p.col_stride;
               }
-              ptx::umma_commit(b_empty(sb));  // frees this weight stage when its MMAs retire
+              if (ptx::elect_one()) ptx::umma_commit(b_empty(sb));  // frees this weight stage when its MMAs retire
+              __syncwarp();
               if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
             }
           }
-          ptx::umma_commit(a_empty(sa));
+          if (ptx::elect_one()) ptx::umma_commit(a_empty(sa));
+          __syncwarp();
           if (++sa == UM_A_STAGES) { sa = 0; pa ^= 1; }
         }
-        ptx::umma_commit(t_full(as));  // accumulators complete -> epilogue
+        if (ptx::elect_one()) ptx::umma_commit(t_full(as));  // accumulators complete -> epilogue
+        __syncwarp();
         if (++as == p.t_stages) { as = 0; ap ^= 1; }
       }
     }
