@@ -199,5 +199,16 @@ def check(rc: int, what: str = "") -> None:
         raise BvgError(f"{what or 'libbvg_b200'} failed (code {rc}): {msg}")
 
 
+_checked_devices = set()
+
+
+def require_sm100(device_index: int) -> None:
+    """Fail loudly unless ``device_index`` is a compute-capability-10.x GPU (checked once per device:
+    cudaGetDeviceProperties costs ~100 ms)."""
+    if device_index not in _checked_devices:
+        check(lib().bvg_device_check(int(device_index)), "device_check")
+        _checked_devices.add(device_index)
+
+
 def set_tuning(name: str, value: int) -> None:
     check(lib().bvg_set_tuning(name.encode(), int(value)), f"set_tuning({name})")

@@ -72,11 +72,12 @@ size_t bvg_sizeof_op(void) { return sizeof(bvg_op); }
 size_t bvg_sizeof_conv_weights(void) { return sizeof(bvg_conv_weights); }
 
 int bvg_device_check(int device) {
-  cudaDeviceProp prop;
-  cudaError_t e = cudaGetDeviceProperties(&prop, device);
-  if (e != cudaSuccess) return bvg::cuda_fail(e, "cudaGetDeviceProperties");
-  if (prop.major != 10) {
-    bvg::set_error("device %d is sm_%d%d; libbvg_b200 is built for sm_100a only (no fallback)", device, prop.major, prop.minor);
+  int major = 0, minor = 0;
+  cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device);
+  if (e != cudaSuccess) return bvg::cuda_fail(e, "cudaDeviceGetAttribute");
+  if (major != 10) {
+    bvg::set_error("device %d is sm_%d%d; libbvg_b200 is built for sm_100a only (no fallback)", device, major, minor);
     return BVG_EARCH;
   }
   return BVG_OK;

@@ -208,6 +208,12 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
 }
 
+// Epilogue specialisation (compile-time, so the per-element code is a handful of instructions):
+//   OUT  : output format (BVG_F32 | BVG_BF16 | BVG_SPLIT)
+//   SBF  : residual / running-sum tensors are bf16 (else fp32)
+//   RES  : a residual is added            ACC : a running sum is added (and maybe divided)
+//   GEN  : generic fallback -- every choice read from the descriptor at run time, ragged N allowed
+template <int OUT, bool SBF, bool RES, bool ACC, bool GEN>
 __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_constant__ UmmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve-up: [A stages][B stages][epilogue staging][barriers][tmem ptr]; base rounded up to 1024 B
@@ -383,7 +389,12 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
     const int rrow = lane >> 2;   // row within an 8-row group after the transposition
     const int g = lane & 3;       // 16-byte granule (4 columns) within the 16-column chunk
     const int n_my = (n_items - grp + 1) >> 1;  // items grp, grp+2, ...
-    const bool res_f32 = p.epi.res_dtype == BVG_F32;
+    const bool has_res = GEN ? (p.epi.res != nullptr) : RES;
+    const bool has_acc = GEN ? (p.epi.acc != nullptr) : ACC;
+    const bool res_bf = GEN ? (p.epi.res_dtype != BVG_F32) : SBF;
+    const bool acc_bf = GEN ? (p.epi.acc_dtype != BVG_F32) : SBF;
+    const int out_dt = GEN ? p.epi.out_dtype : OUT;
+    const int N = p.epi.N;
     int as = 0, ap = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int nt = (int)(tile % p.n_tiles);
@@ -404,20 +415,23 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
           const int mbi = it / n_chunks;
           it_mbi[u] = mbi;
           it_c0[u] = (it - mbi * n_chunks) << 4;
-          const int tbase = t0 + mbi * UM_BM + q * 32;
-          const int n0 = nt * p.n_tile + it_c0[u] + 4 * g;
+          if (has_res && (!GEN || p.vec_ok)) {
+            const int tbase = t0 + mbi * UM_BM + q * 32;
+            const int n0 = nt * p.n_tile + it_c0[u] + 4 * g;
+            const bool ok = pb2 + u < n_my && n0 < N;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            raw[u][i] = make_uint4(0u, 0u, 0u, 0u);
-            const int t = tbase + rrow + 8 * i;
-            if (p.epi.res && p.vec_ok && pb2 + u < n_my && t < p.L && n0 < p.N) {
-              const long long off = (row_base + t) * p.epi.N + n0;
-              if (res_f32) {
-                raw[u][i] = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.epi.res) + off);
-              } else {
-                const uint2 h = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.epi.res) + off);
-                raw[u][i].x = h.x;
-                raw[u][i].y = h.y;
+            for (int i = 0; i < 4; ++i) {
+              raw[u][i] = make_uint4(0u, 0u, 0u, 0u);
+              const int t = tbase + rrow + 8 * i;
+              if (ok && t < p.L) {
+                const long long off = (row_base + t) * N + n0;
+                if (!res_bf) {
+                  raw[u][i] = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.epi.res) + off);
+                } else {
+                  const uint2 h = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.epi.res) + off);
+                  raw[u][i].x = h.x;
+                  raw[u][i].y = h.y;
+                }
               }
             }
           }
@@ -454,36 +468,58 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
             v[i][0] = __uint_as_float(a0); v[i][1] = __uint_as_float(a1); v[i][2] = __uint_as_float(a2); v[i][3] = __uint_as_float(a3);
           }
           __syncwarp();
-          if (n0 >= p.N) continue;
-          if (p.vec_ok) {
+          if (n0 >= N) continue;
+          if (!GEN || p.vec_ok) {
             const float4 bias = *reinterpret_cast<const float4*>(p.epi.bias + n0);
+            const long long off0 = (row_base + tbase + rrow) * N + n0;  // row i adds 8 * i * N
             float ac[4][4];
+            if (has_acc) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int t = tbase + rrow + 8 * i;
+              for (int i = 0; i < 4; ++i) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) ac[i][j] = 0.f;
-              if (p.epi.acc && t < p.L) epi_load4(p.epi.acc, p.epi.acc_dtype, (row_base + t) * p.epi.N + n0, ac[i]);
+                for (int j = 0; j < 4; ++j) ac[i][j] = 0.f;
+                if (tbase + rrow + 8 * i < p.L) epi_load4(p.epi.acc, acc_bf ? BVG_BF16 : BVG_F32, off0 + (long long)(8 * i) * N, ac[i]);
+              }
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const int t = tbase + rrow + 8 * i;
-              if (t >= p.L) continue;
-              float rs[4];
-              if (res_f32) {
-                rs[0] = __uint_as_float(raw[u][i].x); rs[1] = __uint_as_float(raw[u][i].y);
-                rs[2] = __uint_as_float(raw[u][i].z); rs[3] = __uint_as_float(raw[u][i].w);
-              } else {
-                unpack_bf16x2(raw[u][i].x, rs[0], rs[1]);
-                unpack_bf16x2(raw[u][i].y, rs[2], rs[3]);
-              }
+              if (tbase + rrow + 8 * i >= p.L) continue;
               v[i][0] += bias.x; v[i][1] += bias.y; v[i][2] += bias.z; v[i][3] += bias.w;
+              if (has_res) {
+                float rs[4];
+                if (!res_bf) {
+                  rs[0] = __uint_as_float(raw[u][i].x); rs[1] = __uint_as_float(raw[u][i].y);
+                  rs[2] = __uint_as_float(raw[u][i].z); rs[3] = __uint_as_float(raw[u][i].w);
+                } else {
+                  unpack_bf16x2(raw[u][i].x, rs[0], rs[1]);
+                  unpack_bf16x2(raw[u][i].y, rs[2], rs[3]);
+                }
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                v[i][j] = (v[i][j] + rs[j]) + ac[i][j];
-                if (p.epi.use_div) v[i][j] = __fdiv_rn(v[i][j], p.epi.div);
+                for (int j = 0; j < 4; ++j) v[i][j] += rs[j];
               }
-              epi_store4(p.epi, (row_base + t) * p.epi.N + n0, v[i]);
+              if (has_acc) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[i][j] += ac[i][j];
+                if (p.epi.use_div) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) v[i][j] = __fdiv_rn(v[i][j], p.epi.div);
+                }
+              } else if (GEN && p.epi.use_div) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[i][j] = __fdiv_rn(v[i][j], p.epi.div);
+              }
+              const long long off = off0 + (long long)(8 * i) * N;
+              if (out_dt == BVG_F32) {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.epi.out) + off) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+              } else if (out_dt == BVG_BF16) {
+                epi_store_bf16x4(p.epi.out, off, v[i]);
+              } else {
+                float hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) split_bf16(v[i][j], hi[j], lo[j]);
+                epi_store_bf16x4(p.epi.out, off, hi);
+                epi_store_bf16x4(p.epi.out_lo, off, lo);
+              }
             }
           } else {
 #pragma unroll
@@ -682,14 +718,43 @@ int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out) {
   return BVG_OK;
 }
 
-int conv_umma_launch(const UmmaLaunch* l, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    BVG_CHECK_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_LIMIT));
-    attr_set = true;
+typedef void (*UmmaKernel)(const UmmaParams);
+
+// pick the epilogue specialisation for a descriptor (nullptr-free: falls back to the generic one)
+static UmmaKernel select_kernel(const UmmaParams& p) {
+  const EpiParams& e = p.epi;
+  const bool res = e.res != nullptr, acc = e.acc != nullptr;
+  const bool sbf = (res && e.res_dtype == BVG_BF16) || (acc && e.acc_dtype == BVG_BF16);
+  const bool mixed = (res && acc && e.res_dtype != e.acc_dtype);
+  const bool plain = p.vec_ok && !mixed && (acc || !e.use_div) && (!acc || res);
+  if (plain) {
+    if (!sbf) {
+      if (e.out_dtype == BVG_F32 && !res) return conv_umma_kernel<BVG_F32, false, false, false, false>;
+      if (e.out_dtype == BVG_F32 && res && !acc) return conv_umma_kernel<BVG_F32, false, true, false, false>;
+      if (e.out_dtype == BVG_F32 && res && acc) return conv_umma_kernel<BVG_F32, false, true, true, false>;
+      if (e.out_dtype == BVG_SPLIT && !res) return conv_umma_kernel<BVG_SPLIT, false, false, false, false>;
+      if (e.out_dtype == BVG_SPLIT && res && acc) return conv_umma_kernel<BVG_SPLIT, false, true, true, false>;
+    }
+    if (e.out_dtype == BVG_BF16 && !res) return conv_umma_kernel<BVG_BF16, true, false, false, false>;
+    if (sbf && e.out_dtype == BVG_BF16 && res && !acc && e.res_dtype == BVG_BF16) return conv_umma_kernel<BVG_BF16, true, true, false, false>;
+    if (sbf && e.out_dtype == BVG_BF16 && res && acc && e.res_dtype == BVG_BF16) return conv_umma_kernel<BVG_BF16, true, true, true, false>;
   }
+  return conv_umma_kernel<BVG_F32, false, false, false, true>;
+}
+
+int conv_umma_launch(const UmmaLaunch* l, cudaStream_t st) {
   if (l->grid <= 0) return BVG_OK;
-  conv_umma_kernel<<<l->grid, UM_THREADS, l->smem, st>>>(l->p);
+  UmmaKernel k = select_kernel(l->p);
+  // opt in to > 48 KB of dynamic shared memory once per specialisation (cheap, idempotent)
+  static UmmaKernel configured[16];
+  static int n_configured = 0;
+  bool seen = false;
+  for (int i = 0; i < n_configured; ++i) seen = seen || configured[i] == k;
+  if (!seen) {
+    BVG_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_LIMIT));
+    if (n_configured < 16) configured[n_configured++] = k;
+  }
+  k<<<l->grid, UM_THREADS, l->smem, st>>>(l->p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "conv_umma_kernel launch");
   return BVG_OK;

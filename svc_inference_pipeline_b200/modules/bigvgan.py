@@ -294,7 +294,7 @@ class Generator(nn.Module):
                 "svc_inference_pipeline_b200.Generator has no CPU path: move the model to a B200 "
                 "(cfg.device = 'cuda' in vocoder_model_loader, or model.cuda())"
             )
-        L.check(L.lib().bvg_device_check(dev.index if dev.index is not None else torch.cuda.current_device()), "device_check")
+        L.require_sm100(dev.index if dev.index is not None else torch.cuda.current_device())
         return dev
 
     def _act_params(self, a1d: _Activation1d):
