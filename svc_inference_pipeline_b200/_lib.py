@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbvg_b200.so")
+# BVG_B200_LIB: A/B-test another build of the same library (development aid; never a fallback)
+LIB_PATH = os.environ.get("BVG_B200_LIB") or os.path.join(_HERE, "libbvg_b200.so")
 
 F32, BF16, SPLIT = 0, 1, 2
 SIMT, UMMA = 0, 1

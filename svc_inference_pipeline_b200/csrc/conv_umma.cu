@@ -60,6 +60,7 @@ struct UmmaParams {
   int col_stride;       // TMEM columns per accumulator (n_tile rounded up to 32)
   int t_stages;         // accumulator stages (each mb * col_stride columns)
   int b_stages;
+  int tap_group;        // taps per weight stage (one TMA box of tap_group * n_tile rows)
   int a_stage_bytes;    // all planes
   int a_plane_bytes;
   int b_stage_bytes;
@@ -208,6 +209,40 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
 }
 
+// MMAs of one weight stage: gtaps taps x mb M blocks x KS K steps (twice with the lo plane of a
+// SPLIT activation).  The issuing warp executes a few instructions per tcgen05.mma at one dependent
+// uniform-datapath instruction every ~4-5 cycles, so for narrow N (an N = 32 MMA lasts 16-40 cycles)
+// and for single-M-block tiles this warp is on the critical path (ncu, v5: 89 cycles per MMA at 20
+// instructions each): K steps are compile-time, the accumulate flag is a predicate, descriptors
+// advance by immediate adds, and the row shift of the next tap is fetched before this tap's MMAs.
+//   sh      : shift of the first tap of the stage (prefetched by the caller, before the barrier wait)
+//   nxt_tap : tap whose shift is to be returned for the caller's next stage
+template <int KS, bool WITH_LO>
+__device__ __forceinline__ int issue_stage(const UmmaParams& p, const int* __restrict__ shifts, int g0, int gtaps, int sh, int nxt_tap,
+                                           int min_shift, uint32_t a_stage16, uint32_t b16, uint32_t tmem_acc, uint32_t a_plane16, uint32_t idesc,
+                                           uint64_t desc_hi, uint32_t acc0, uint32_t b_tap16, uint32_t col_stride, int mb) {
+  for (int g = 0; g < gtaps; ++g) {
+    uint32_t a16 = a_stage16 + (uint32_t)(sh - min_shift) * 8u;  // 128 B per row
+    sh = shifts[g + 1 < gtaps ? g0 + g + 1 : nxt_tap];
+    uint32_t tmem_d = tmem_acc;
+    const uint32_t first = g == 0 ? acc0 : 1u;
+    for (int mbi = 0; mbi < mb; ++mbi) {
+#pragma unroll
+      for (int k = 0; k < KS; ++k) {
+        const uint64_t bd = desc_hi | (uint64_t)(b16 + 2u * k);
+        if (ptx::elect_one()) ptx::umma_f16(tmem_d, desc_hi | (uint64_t)(a16 + 2u * k), bd, idesc, k == 0 ? first : 1u);
+        if (WITH_LO) {
+          if (ptx::elect_one()) ptx::umma_f16(tmem_d, desc_hi | (uint64_t)(a16 + a_plane16 + 2u * k), bd, idesc, 1u);
+        }
+      }
+      a16 += (UM_BM * 128u) >> 4;
+      tmem_d += col_stride;
+    }
+    b16 += b_tap16;
+  }
+  return sh;
+}
+
 // Epilogue specialisation (compile-time, so the per-element code is a handful of instructions):
 //   OUT  : output format (BVG_F32 | BVG_BF16 | BVG_SPLIT)
 //   SBF  : residual / running-sum tensors are bf16 (else fp32)
@@ -297,13 +332,15 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
           }
           __syncwarp();
           if (++sa == UM_A_STAGES) { sa = 0; pa ^= 1; }
-          for (int slot = 0; slot < ntaps; ++slot) {
+          // weights: one box of tap_group consecutive taps per (group, plane); rows past the last
+          // tap of this N tile belong to the next tile (or are zero-filled past the end) and are unused
+          for (int g0 = 0; g0 < ntaps; g0 += p.tap_group) {
             for (int wp = 0; wp < planes; ++wp) {
               ptx::mbar_wait(b_empty(sb), pb ^ 1, p.err_flag, 2);
               if (ptx::elect_one()) {
                 ptx::mbar_expect_tx(b_full(sb), (uint32_t)p.b_stage_bytes);
                 ptx::tma_load_2d(b_base + sb * p.b_stage_bytes, &p.tm_w[wp], b_full(sb), cb * UM_KB,
-                                 (nt * p.tap_stride + slot) * p.n_tile);
+                                 (nt * p.tap_stride + g0) * p.n_tile);
               }
               __syncwarp();
               if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
@@ -325,6 +362,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
       const uint64_t desc_hi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;  // SBO, version, SWIZZLE_128B
       const uint32_t a_plane16 = (uint32_t)p.a_plane_bytes >> 4;
       const bool split = p.planes == 2;
+      const int tap_group = p.tap_group;
+      const int mb = p.mb;
+      const uint32_t b_tap16 = (uint32_t)p.n_tile * 8u;  // n_tile rows of 128 B per tap
+      const uint32_t col_stride = (uint32_t)p.col_stride;
+      const int ks_last = (p.cin - (p.n_cb - 1) * UM_KB + 15) >> 4;
       int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, ap = 0;
       for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int nt = (int)(tile % p.n_tiles);
@@ -333,37 +375,41 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
         ptx::mbar_wait(t_empty(as), ap ^ 1, p.err_flag, 3);
         ptx::tc_fence_after();
         const uint32_t tmem_acc = tmem_base + (uint32_t)(as * stage_cols);
+        const int* shifts = p.shift[nt];
+        int sh = shifts[0];
         for (int cb = 0; cb < p.n_cb; ++cb) {
-          const int valid = min(UM_KB, p.cin - cb * UM_KB);
-          const int ksteps = (valid + 15) >> 4;
+          const int ksteps = cb + 1 < p.n_cb ? 4 : ks_last;
           ptx::mbar_wait(a_full(sa), pa, p.err_flag, 4);
           const uint32_t a_stage16 = (((a_base + sa * p.a_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
-          for (int slot = 0; slot < ntaps; ++slot) {
-            const uint32_t a_tap16 = a_stage16 + (uint32_t)(p.shift[nt][slot] - min_shift) * 8u;  // 128 B per row
-            for (int wp = 0; wp < planes; ++wp) {
-              ptx::mbar_wait(b_full(sb), pb, p.err_flag, 5);
-              ptx::tc_fence_after();
-              const uint32_t b16 = (((b_base + sb * p.b_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
-              const uint32_t first = (cb == 0 && slot == 0 && wp == 0) ? 0u : 1u;  // 0 => overwrite the accumulator
-              const bool with_lo = split && wp == 0;
-              uint32_t a16 = a_tap16;
-              uint32_t tmem_d = tmem_acc;
-              for (int mbi = 0; mbi < p.mb; ++mbi) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  if (k < ksteps) {
-                    const uint64_t bd = desc_hi | (uint64_t)(b16 + 2u * k);
-                    if (ptx::elect_one()) ptx::umma_f16(tmem_d, desc_hi | (uint64_t)(a16 + 2u * k), bd, idesc, k == 0 ? first : 1u);
-                    if (with_lo && ptx::elect_one()) ptx::umma_f16(tmem_d, desc_hi | (uint64_t)(a16 + a_plane16 + 2u * k), bd, idesc, 1u);
-                  }
-                }
-                a16 += (UM_BM * 128u) >> 4;
-                tmem_d += (uint32_t)p.col_stride;
-              }
-              if (ptx::elect_one()) ptx::umma_commit(b_empty(sb));  // frees this weight stage when its MMAs retire
-              __syncwarp();
-              if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+          for (int g0 = 0; g0 < ntaps; g0 += tap_group) {
+            const int gtaps = min(tap_group, ntaps - g0);
+            const int g_next = g0 + tap_group < ntaps ? g0 + tap_group : 0;
+            const uint32_t acc0 = (cb == 0 && g0 == 0) ? 0u : 1u;  // 0 => the first tap overwrites the accumulator
+            // one straight-line body per (K steps, lo plane) combination, chosen once per stage
+#define BVG_ISSUE(KS, LO, NXT, ACC)                                                                                                          \
+  sh = issue_stage<KS, LO>(p, shifts, g0, gtaps, sh, NXT, min_shift, a_stage16, b16, tmem_acc, a_plane16, idesc, desc_hi, ACC, b_tap16, \
+                           col_stride, mb)
+#define BVG_STAGE(LO, NXT, ACC)                                                              \
+  {                                                                                          \
+    ptx::mbar_wait(b_full(sb), pb, p.err_flag, 5);                                           \
+    ptx::tc_fence_after();                                                                   \
+    const uint32_t b16 = (((b_base + sb * p.b_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);   \
+    if (ksteps == 4) BVG_ISSUE(4, LO, NXT, ACC);                                             \
+    else if (ksteps == 2) BVG_ISSUE(2, LO, NXT, ACC);                                        \
+    else if (ksteps == 3) BVG_ISSUE(3, LO, NXT, ACC);                                        \
+    else BVG_ISSUE(1, LO, NXT, ACC);                                                         \
+    if (ptx::elect_one()) ptx::umma_commit(b_empty(sb)); /* frees the stage when its MMAs retire */ \
+    __syncwarp();                                                                            \
+    if (++sb == p.b_stages) { sb = 0; pb ^= 1; }                                             \
+  }
+            if (split) {
+              BVG_STAGE(true, g0, acc0);       // W hi: A hi and A lo
+              BVG_STAGE(false, g_next, 1u);    // W lo: A hi
+            } else {
+              BVG_STAGE(false, g_next, acc0);
             }
+#undef BVG_STAGE
+#undef BVG_ISSUE
           }
           if (ptx::elect_one()) ptx::umma_commit(a_empty(sa));
           __syncwarp();
@@ -589,20 +635,23 @@ static int encode_bf16_map(CUtensorMap* map, void* base, int rank, const cuuint6
   return BVG_OK;
 }
 
-int umma_mb = 0;         // tuning/test hook: force M blocks per tile (0 = choose)
-int umma_wide_mb2 = 0;   // tuning/test hook: allow mb = 2 with a single TMEM stage for 256-column tiles
-int umma_max_ctas = 0;   // tuning/test hook: cap the persistent grid
-
 struct UmmaLaunch {
   UmmaParams p;
   int grid;
   size_t smem;
 };
 
+int umma_mb = 0;         // tuning/test hook: force M blocks per tile (0 = choose)
+int umma_wide_mb2 = 0;   // tuning/test hook: allow mb = 2 with a single TMEM stage for 256-column tiles
+int umma_max_ctas = 0;   // tuning/test hook: cap the persistent grid
+int umma_tap_group = 0;  // tuning/test hook: taps per weight stage (0 = choose)
+
 static const int kBarBytes = 8 * (2 * UM_A_STAGES + 2 * UM_MAX_B_STAGES + 2 * UM_MAX_T_STAGES) + 16;
 
-// shared-memory plan for a given number of M blocks; returns the number of weight stages that fit
-static int plan_smem(int mb, int max_span, int planes, int n_tile, int* box_rows, int* boxes) {
+// shared-memory plan for a given number of M blocks: picks the taps per weight stage (narrow N
+// tiles group several taps into one TMA box / one barrier round trip) and returns the number of
+// weight stages that fit
+static int plan_smem(int mb, int max_span, int planes, int n_tile, int max_taps, int* box_rows, int* boxes, int* tap_group) {
   const int rows = mb * UM_BM + max_span;
   const int nb = (rows + 255) / 256;
   const int br = (((rows + nb - 1) / nb) + 7) / 8 * 8;
@@ -611,7 +660,13 @@ static int plan_smem(int mb, int max_span, int planes, int n_tile, int* box_rows
   const int a_stage = nb * br * 128 * planes;
   const int avail = UM_SMEM_LIMIT - 1024 - kBarBytes - UM_STAGING_BYTES - UM_A_STAGES * a_stage;
   if (avail <= 0) return 0;
-  int bs = avail / (n_tile * 128);
+  int g = umma_tap_group > 0 ? umma_tap_group : 24 * 1024 / (n_tile * 128);  // ~24 KB per stage
+  if (g > 256 / n_tile) g = 256 / n_tile;                                      // TMA box <= 256 rows
+  if (g > max_taps) g = max_taps;
+  if (g < 1) g = 1;
+  while (g > 1 && avail / (g * n_tile * 128) < 3) --g;
+  *tap_group = g;
+  int bs = avail / (g * n_tile * 128);
   return bs > UM_MAX_B_STAGES ? UM_MAX_B_STAGES : bs;
 }
 
@@ -642,8 +697,9 @@ int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out) {
   p.n_cb = w->cin_pad / UM_KB;
   p.cin = w->cin;
   p.vec_ok = (w->n_total % 4 == 0) ? 1 : 0;
-  int max_span = 0;
+  int max_span = 0, max_taps = 1;
   for (int t = 0; t < w->n_tiles; ++t) {
+    if (w->n_taps[t] > max_taps) max_taps = w->n_taps[t];
     BVG_REQUIRE(w->n_taps[t] > 0 && w->n_taps[t] <= BVG_MAX_TAPS, "conv_umma: bad tap count");
     int lo = w->shift[t][0], hi = w->shift[t][0];
     for (int k = 0; k < w->n_taps[t]; ++k) {
@@ -667,10 +723,10 @@ int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out) {
   p.col_stride = (w->n_tile + 31) / 32 * 32;
   int mb = 1;
   for (int cand = UM_MAX_MB; cand >= 1; cand >>= 1) {
-    int br, nb;
+    int br, nb, tg;
     const bool tmem_ok = cand * p.col_stride * 2 <= 512 || (cand == 1) || (umma_wide_mb2 && cand == 2 && cand * p.col_stride <= 512);
     if (!tmem_ok) continue;
-    if (plan_smem(cand, max_span, planes, w->n_tile, &br, &nb) < (cand == 1 ? 2 : 3)) continue;
+    if (plan_smem(cand, max_span, planes, w->n_tile, max_taps, &br, &nb, &tg) < (cand == 1 ? 2 : 3)) continue;
     const long long tiles = (long long)d->B * ceil_div(d->L, cand * UM_BM) * w->n_tiles;
     if (cand > 1 && tiles < 2ll * sms) continue;
     mb = cand;
@@ -684,12 +740,12 @@ int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out) {
   p.total_tiles = (long long)d->B * p.m_tiles_per_item * w->n_tiles;
   p.t_stages = 512 / (mb * p.col_stride);
   if (p.t_stages > UM_MAX_T_STAGES) p.t_stages = UM_MAX_T_STAGES;
-  const int bs = plan_smem(mb, max_span, planes, w->n_tile, &p.a_box_rows, &p.a_boxes);
+  const int bs = plan_smem(mb, max_span, planes, w->n_tile, max_taps, &p.a_box_rows, &p.a_boxes, &p.tap_group);
   BVG_REQUIRE(bs >= 2, "conv_umma: tile does not fit in shared memory (mb %d, span %d, n_tile %d, planes %d)", mb, max_span, w->n_tile, planes);
   p.b_stages = bs;
   p.a_plane_bytes = p.a_boxes * p.a_box_rows * 128;
   p.a_stage_bytes = p.a_plane_bytes * planes;
-  p.b_stage_bytes = w->n_tile * 128;
+  p.b_stage_bytes = p.tap_group * w->n_tile * 128;
   size_t smem = 1024 + (size_t)UM_A_STAGES * p.a_stage_bytes + (size_t)bs * p.b_stage_bytes + UM_STAGING_BYTES + kBarBytes;
   // keep one CTA per SM (each allocates all 512 TMEM columns): ask for more than half the SM's smem
   if (smem < 120 * 1024) smem = 120 * 1024;
@@ -707,7 +763,7 @@ int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out) {
     void* wb = pl == 0 ? w->d_w : w->d_w_lo;
     cuuint64_t wdims[2] = {(cuuint64_t)w->cin_pad, (cuuint64_t)w->n_tiles * w->tap_stride * w->n_tile};
     cuuint64_t wstrides[1] = {(cuuint64_t)w->cin_pad * 2};
-    cuuint32_t wbox[2] = {(cuuint32_t)UM_KB, (cuuint32_t)w->n_tile};
+    cuuint32_t wbox[2] = {(cuuint32_t)UM_KB, (cuuint32_t)(p.tap_group * w->n_tile)};
     rc = encode_bf16_map(&p.tm_w[pl], wb, 2, wdims, wstrides, wbox, "weights");
     if (rc != BVG_OK) return rc;
   }
