@@ -231,6 +231,177 @@ __global__ void __launch_bounds__(128) amp_kernel(const __grid_constant__ AmpPar
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Packed variant for two channels per thread: Blackwell's FFMA2 / FMUL2 / FADD2 (PTX fma.rn.f32x2 ...)
+// execute two fp32 lanes per instruction and take a scalar (broadcast) operand, so every FIR tap is
+// ONE instruction for both channels.  ncu on the scalar kernel: 85 % issue-active at 60 instructions
+// per element -- the issue slots, not HBM, bound it; this halves the FIR and most of the snake.
+// Each lane of an f32x2 operation is an IEEE fp32 operation, so results are bit-identical to the
+// scalar kernel above.
+// ------------------------------------------------------------------------------------------------
+typedef unsigned long long P2;  // two packed fp32 (channel c in the low half, c+1 in the high half)
+
+__device__ __forceinline__ P2 pk2(float a, float b) {
+  P2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(P2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ P2 fma2(P2 a, P2 b, P2 c) {
+  P2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ P2 mul2(P2 a, P2 b) {
+  P2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ P2 add2(P2 a, P2 b) {
+  P2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+template <bool IN_BF16>
+__device__ __forceinline__ P2 load_row2(const void* base, long long off) {
+  if constexpr (!IN_BF16) {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(base) + off));
+    return pk2(t.x, t.y);
+  } else {
+    const uint32_t t = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(base) + off));
+    return pk2(__uint_as_float(t << 16), __uint_as_float(t & 0xffff0000u));
+  }
+}
+
+// same operation order as snake_one, two channels at a time (apar = a or a/pi, see snake_one)
+template <bool FAST_SIN>
+__device__ __forceinline__ P2 snake_two(P2 u, P2 apar, P2 invb) {
+  P2 arg = mul2(u, apar);
+  if constexpr (!FAST_SIN) {
+    const P2 magic = pk2(12582912.0f, 12582912.0f), nmagic = pk2(-12582912.0f, -12582912.0f);
+    const P2 k = add2(add2(arg, magic), nmagic);              // rint for |t| < 2^22
+    arg = fma2(k, pk2(-1.0f, -1.0f), arg);                     // [-0.5, 0.5] half-turns (exact)
+    arg = mul2(arg, pk2(3.14159265358979f, 3.14159265358979f));
+  }
+  float a0, a1;
+  upk2(arg, a0, a1);
+  const P2 s = pk2(__sinf(a0), __sinf(a1));
+  return fma2(invb, mul2(s, s), u);
+}
+
+template <bool IN_BF16, int OUT_MODE, bool FAST_SIN, bool STORE>
+__device__ __forceinline__ void amp_block6_p2(const AmpParams& p, const P2 (&xa)[6], P2 (&xb)[6], const P2 (&sa)[12], P2 (&sb)[12], int tau0,
+                                              long long base, P2 apar, P2 invb) {
+  const int L = p.L;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const int r = min(max(tau0 + 6 + j, 0), L - 1);
+    xb[j] = load_row2<IN_BF16>(p.x, base + (long long)r * p.C);
+  }
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    P2 pa = 0ull, pb = 0ull;  // +0.0f in both lanes
+#pragma unroll
+    for (int m = 0; m < 6; ++m) {
+      const int w = j + 5 - m;  // window slot of x[tau + 5 - m]
+      const P2 xv = (w < 6) ? xa[w < 6 ? w : 0] : xb[w >= 6 ? w - 6 : 0];
+      pb = fma2(pk2(p.gu[2 * m + 1], p.gu[2 * m + 1]), xv, pb);  // s[2 tau + 6]: even phase, i = tau + 3
+      pa = fma2(pk2(p.gu[2 * m], p.gu[2 * m]), xv, pa);          // s[2 tau + 5]: odd phase,  i = tau + 2
+    }
+    pa = snake_two<FAST_SIN>(pa, apar, invb);
+    pb = snake_two<FAST_SIN>(pb, apar, invb);
+    const int tau = tau0 + j;
+    if (tau >= L - 3) {  // right replicate clamp of the activated signal: s[j > 2L-1] = s[2L-1]
+      const P2 prev = (j == 0) ? sa[11] : sb[j == 0 ? 0 : 2 * j - 1];
+      if (tau >= L - 2) pa = prev;
+      pb = pa;
+    }
+    sb[2 * j] = pa;
+    sb[2 * j + 1] = pb;
+    if constexpr (STORE) {
+      P2 z = 0ull;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        const int i = 2 * j + 2 + k;  // slot in (sa ++ sb) of s[2 tau - 5 + k]
+        const P2 sv = (i < 12) ? sa[i < 12 ? i : 0] : sb[i >= 12 ? i - 12 : 0];
+        z = fma2(pk2(p.fd[k], p.fd[k]), sv, z);
+      }
+      if (tau < L) {
+        float zz[2];
+        upk2(z, zz[0], zz[1]);
+        store_row<OUT_MODE, 2>(p.y, p.y_lo, base + (long long)tau * p.C, zz);
+      }
+    }
+  }
+}
+
+template <bool IN_BF16, int OUT_MODE, bool FAST_SIN>
+__global__ void __launch_bounds__(128) amp_kernel_p2(const __grid_constant__ AmpParams p) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= p.total_threads) return;
+  const int cg = (int)(tid % p.CG);
+  const long long rest = tid / p.CG;
+  const int chunk = (int)(rest % p.nchunks);
+  const int b = (int)(rest / p.nchunks);
+  const int TT = 12 * p.nblk2;
+  const int t0 = chunk * TT;
+  const int L = p.L;
+  const long long base = (long long)b * L * p.C + (long long)cg * 2;
+
+  const float a0 = __ldg(p.a + cg * 2), a1 = __ldg(p.a + cg * 2 + 1);
+  const P2 apar = FAST_SIN ? pk2(a0, a1) : pk2(a0 * 0.318309886183790672f, a1 * 0.318309886183790672f);
+  const P2 invb = pk2(__ldg(p.invb + cg * 2), __ldg(p.invb + cg * 2 + 1));
+
+  P2 xa[6], xb[6], sa[12], sb[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) sa[k] = 0ull;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const int r = min(max(t0 - 6 + k, 0), L - 1);
+    xa[k] = load_row2<IN_BF16>(p.x, base + (long long)r * p.C);
+  }
+  // warm-up block (tau = t0-6 .. t0-1): fills sb = s[2 t0 - 7 .. 2 t0 + 4], no output
+  amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, false>(p, xa, xb, sa, sb, t0 - 6, base, apar, invb);
+  if (t0 == 0) {  // left replicate clamp of the activated signal: s[j < 0] = s[0] (slot 7)
+#pragma unroll
+    for (int k = 0; k < 7; ++k) sb[k] = sb[7];
+  }
+  int t = t0;
+  for (int i = 0; i < p.nblk2; ++i) {
+    if (t >= L) break;
+    amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, true>(p, xb, xa, sb, sa, t, base, apar, invb);
+    t += 6;
+    if (t >= L) break;
+    amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, true>(p, xa, xb, sa, sb, t, base, apar, invb);
+    t += 6;
+  }
+}
+
+int amp_packed_enable = 1;  // test/tuning hook ("amp_packed"): 0 = scalar FFMA kernel for two channels per thread too
+
+template <bool IN_BF16, int OUT_MODE>
+static cudaError_t launch_amp_p2(const AmpParams& p, bool fast, cudaStream_t st) {
+  const int threads = 128;
+  const long long blocks = ceil_div_ll(p.total_threads, threads);
+  if (fast)
+    amp_kernel_p2<IN_BF16, OUT_MODE, true><<<(unsigned)blocks, threads, 0, st>>>(p);
+  else
+    amp_kernel_p2<IN_BF16, OUT_MODE, false><<<(unsigned)blocks, threads, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_amp_packed(const AmpParams& p, bool in_bf16, int out_mode, bool fast, cudaStream_t st) {
+  if (in_bf16) {
+    if (out_mode == BVG_F32) return launch_amp_p2<true, BVG_F32>(p, fast, st);
+    if (out_mode == BVG_BF16) return launch_amp_p2<true, BVG_BF16>(p, fast, st);
+    return launch_amp_p2<true, BVG_SPLIT>(p, fast, st);
+  }
+  if (out_mode == BVG_F32) return launch_amp_p2<false, BVG_F32>(p, fast, st);
+  if (out_mode == BVG_BF16) return launch_amp_p2<false, BVG_BF16>(p, fast, st);
+  return launch_amp_p2<false, BVG_SPLIT>(p, fast, st);
+}
+
 template <bool IN_BF16, int OUT_MODE, int VEC, bool FAST_SIN>
 static cudaError_t launch_amp(const AmpParams& p, cudaStream_t st) {
   const int threads = 128;
@@ -256,6 +427,9 @@ static cudaError_t launch_amp_vec(const AmpParams& p, bool in_bf16, int out_mode
   return launch_amp_sin<false, BVG_SPLIT, VEC>(p, fast, st);
 }
 
+bool amp_mma_supported(const bvg_amp_desc* d);               // amp_mma.cu: tensor-core FIR variant
+int amp_mma_forward(const bvg_amp_desc* d, cudaStream_t st);
+
 int amp_vec_override = 0;  // test/tuning hook: force VEC (set through bvg_set_tuning)
 int amp_chunk_override = 0;
 
@@ -267,6 +441,10 @@ int amp_forward(const bvg_amp_desc* d, cudaStream_t st) {
   BVG_REQUIRE(d->y.dtype >= BVG_F32 && d->y.dtype <= BVG_SPLIT, "amp: bad output dtype");
   BVG_REQUIRE(d->y.dtype != BVG_SPLIT || d->y.d_lo, "amp: SPLIT output needs a lo plane");
   BVG_REQUIRE((long long)d->L * d->C < (1ll << 31), "amp: L*C too large for one batch item");
+
+  // the two operand formats of the generator (F32 -> SPLIT, BF16 -> BF16) run the FIRs on the
+  // tensor cores; every other combination stays on the FFMA kernel below
+  if (amp_mma_supported(d)) return amp_mma_forward(d, st);
 
   // two channels per thread: measured 15-25 % faster than four on B200 (64 vs 164 registers ->
   // 2.7x the resident warps; profiles/r01_amp_sweep.txt)
@@ -302,6 +480,8 @@ int amp_forward(const bvg_amp_desc* d, cudaStream_t st) {
   const bool in_bf16 = d->x.dtype == BVG_BF16;
   if (vec == 4)
     e = launch_amp_vec<4>(p, in_bf16, d->y.dtype, d->fast_sin != 0, st);
+  else if (vec == 2 && amp_packed_enable)
+    e = launch_amp_packed(p, in_bf16, d->y.dtype, d->fast_sin != 0, st);
   else if (vec == 2)
     e = launch_amp_vec<2>(p, in_bf16, d->y.dtype, d->fast_sin != 0, st);
   else

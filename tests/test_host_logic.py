@@ -159,3 +159,11 @@ def test_no_product_import_of_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_amp_mma_index_math():
+    """Lane-level emulation of the tensor-core Activation1d kernel (amp_mma.cu): Toeplitz fragments,
+    fragment chaining, tile offsets and both replicate clamps reproduce the oracle exactly."""
+    import amp_mma_emulation as E
+
+    assert E.main(lengths=(1, 2, 3, 4, 7, 8, 9, 12, 13, 16, 20, 31, 32, 33, 67), verbose=False) < 1e-12
