@@ -162,14 +162,45 @@ int bvg_pack_post_weights(const float* d_v, const float* d_g, int32_t cin, int32
                           float* d_scratch /* >= 1 float */, void* stream);
 
 /* Head: mel [B, C, T] float (reference layout, modules/bigvgan.py:600) -> channels-last operand
- * [B, T, c_pad] (F32, BF16 or SPLIT), zero-filling channels C..c_pad-1. */
+ * [B, T, c_pad] (F32, BF16 or SPLIT), zero-filling channels C..c_pad-1.
+ * Optional fused de-normalisation (replaces denormalize_mel_channel,
+ * utils/acoustic_feature_extraction.py:83-97, the step infer.py:80 runs on the host between the
+ * acoustic model and the vocoder): when d_range != NULL the kernel reads a mel normalised to
+ * [-1, 1] and forms ((mel + 1) / 2) * d_range[c] + d_min[c] in fp32, one rounding per operation like
+ * the reference's numpy expression, with d_range[c] = mel_max[c] - mel_min[c] + 1e-12. */
 typedef struct bvg_pack_desc {
   const float* d_mel;
   bvg_tensor out;
   int32_t B, C, T, c_pad;
+  const float* d_range; /* [C] or NULL */
+  const float* d_min;   /* [C] or NULL */
 } bvg_pack_desc;
 
 int bvg_pack_mel(const bvg_pack_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Waveform tail: what infer.py:86-90 does on the host after the
+ * vocoder -- synthesis_audios' fade-out (modules/bigvgan_inference.py:37-42: the last fade_len =
+ * 20 * hop_length samples times torch.linspace(1, 0, fade_len)) and save_audio's peak
+ * normalisation to volume_peak, 50 ms of leading / trailing silence and 16-bit PCM quantisation
+ * (utils/util.py:20-37) -- fused into two kernels, so the device -> host copy is int16.
+ *   d_wave: float [B, L] generator output (not modified);  d_pcm: int16 [B, silence + L + silence];
+ *   d_peak: float [B] scratch, receives max |faded wave| per item.
+ * PCM convention: clamp(rint(v * 32768), -32768, 32767) (torchaudio's encoder is not importable in
+ * this image, so the quantiser is stated, not pinned).  A silent item (peak 0) stays silent.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct bvg_tail_desc {
+  const float* d_wave;
+  int16_t* d_pcm;
+  float* d_peak;
+  int32_t B, L;
+  int32_t fade_len;   /* 0 = no fade; must be <= L (the reference fails for T < 20 frames) */
+  int32_t silence;    /* samples of silence on each side (fs / 20 in save_audio; 0 = none) */
+  float volume_peak;  /* 0.9 in save_audio; <= 0 = no peak normalisation ("turn_up=False") */
+  int32_t _pad;
+} bvg_tail_desc;
+
+int bvg_tail_fwd(const bvg_tail_desc* d, void* stream);
 
 /* Layout/format helpers used by tests and by the sharded stitch. */
 int bvg_convert(const bvg_tensor* src, const bvg_tensor* dst, size_t n_elems, void* stream);

@@ -304,3 +304,54 @@ def synthesis_tail(audio: np.ndarray, frames: int, hop_length: int) -> np.ndarra
     fade = np.linspace(1.0, 0.0, 20 * hop_length, dtype=np.float32)
     audio[-20 * hop_length :] *= fade  # raises on frames < 20 exactly like the reference's broadcast
     return audio
+
+
+# --------------------------------------------------------------------------------------
+# section 8f row 1: the host steps either side of the vocoder in infer.py:80-90
+# --------------------------------------------------------------------------------------
+
+
+def denormalize_mel_channel(mel: np.ndarray, mel_min: np.ndarray, mel_max: np.ndarray) -> np.ndarray:
+    """``denormalize_mel_channel`` (utils/acoustic_feature_extraction.py:83-97): ``mel`` [n_mels, T] (or
+    [B, n_mels, T]) in [-1, 1] -> ``(mel + 1) / 2 * (mel_max - mel_min + 1e-12) + mel_min``, evaluated
+    in float32 with one rounding per operation (numpy semantics for float32 arrays and python scalars)."""
+    f = np.float32
+    mel = mel.astype(f)
+    mn = mel_min.astype(f)[..., :, None]
+    rng = (mel_max.astype(f) - mel_min.astype(f) + f(1e-12)).astype(f)[..., :, None]
+    return ((((mel + f(1.0)) * f(0.5)).astype(f) * rng).astype(f) + mn).astype(f)
+
+
+def linspace_1_0(n: int) -> np.ndarray:
+    """``torch.linspace(1, 0, steps=n)`` in float32, scalar formulation of ATen's CPU kernel
+    (RangeFactoriesKernel: ``step = (end - start) / (n - 1)``; first half ``start + step * i``, second
+    half ``end - step * (n - 1 - i)``).  ATen's *vectorised* path forms ``base + step * lane`` per SIMD
+    chunk, so ``torch.linspace`` itself differs from this by at most one ulp on some entries, depending
+    on the host's vector width (tests/test_oracle_golden.py::test_linspace_restates_torch)."""
+    f = np.float32
+    if n == 1:
+        return np.ones(1, dtype=f)
+    step = f(f(-1.0) / f(n - 1))
+    i = np.arange(n)
+    up = (f(1.0) + (step * i.astype(f)).astype(f)).astype(f)
+    dn = (f(0.0) - (step * (n - 1 - i).astype(f)).astype(f)).astype(f)
+    return np.where(i < n // 2, up, dn).astype(f)
+
+
+def synthesis_pcm16(audio: np.ndarray, hop_length: int, fs: int, add_silence=True, turn_up=True, volume_peak=0.9) -> np.ndarray:
+    """``synthesis_audios`` fade-out (modules/bigvgan_inference.py:37-42) followed by ``save_audio``'s
+    waveform processing (utils/util.py:20-37) and 16-bit quantisation ``clip(rint(v * 32768))``, on one
+    float32 waveform ``[T * hop]``.  ``volume_peak / peak`` is a float32 division (numpy >= 2 scalar
+    rules).  The quantiser of ``torchaudio.save(..., encoding="PCM_S", bits_per_sample=16)`` is not
+    importable in this image (needs torchcodec): stated, not pinned."""
+    f = np.float32
+    w = audio.astype(f).copy()
+    n = 20 * hop_length
+    w[-n:] = (w[-n:] * linspace_1_0(n)).astype(f)
+    if turn_up:
+        peak = f(max(w.max(), abs(w.min())))
+        w = (w * f(f(volume_peak) / peak)).astype(f) if peak > 0 else np.zeros_like(w)
+    if add_silence:
+        s = np.zeros(fs // 20, dtype=f)
+        w = np.concatenate([s, w, s])
+    return np.clip(np.rint((w * f(32768.0)).astype(f)), -32768, 32767).astype(np.int16)

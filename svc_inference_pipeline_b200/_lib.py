@@ -109,6 +109,22 @@ class PackDesc(C.Structure):
         ("C", C.c_int32),
         ("T", C.c_int32),
         ("c_pad", C.c_int32),
+        ("d_range", C.c_void_p),
+        ("d_min", C.c_void_p),
+    ]
+
+
+class TailDesc(C.Structure):
+    _fields_ = [
+        ("d_wave", C.c_void_p),
+        ("d_pcm", C.c_void_p),
+        ("d_peak", C.c_void_p),
+        ("B", C.c_int32),
+        ("L", C.c_int32),
+        ("fade_len", C.c_int32),
+        ("silence", C.c_int32),
+        ("volume_peak", C.c_float),
+        ("_pad", C.c_int32),
     ]
 
 
@@ -137,6 +153,7 @@ EXPORTS = [
     "bvg_post_fwd",
     "bvg_pack_post_weights",
     "bvg_pack_mel",
+    "bvg_tail_fwd",
     "bvg_convert",
     "bvg_program_create",
     "bvg_program_run",
@@ -169,6 +186,7 @@ def lib():
         "bvg_conv_fwd": [C.POINTER(ConvDesc), C.c_void_p],
         "bvg_post_fwd": [C.POINTER(PostDesc), C.c_void_p],
         "bvg_pack_mel": [C.POINTER(PackDesc), C.c_void_p],
+        "bvg_tail_fwd": [C.POINTER(TailDesc), C.c_void_p],
         "bvg_convert": [C.POINTER(Tensor), C.POINTER(Tensor), C.c_size_t, C.c_void_p],
         "bvg_conv_geometry": [C.POINTER(ConvGeom), C.POINTER(ConvWeights)],
         "bvg_conv_pack_bytes": [C.POINTER(ConvGeom), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)],

@@ -404,16 +404,19 @@ static cudaError_t launch_amp_mma_ng(const AmpMmaParams& p, int ng, cudaStream_t
 }
 
 int amp_mma_tiles = 0;   // test/tuning hook ("amp_mma_tiles"): time tiles per CTA, 0 = choose
-int amp_mma_enable = 1;  // test/tuning hook (bvg_set_tuning "amp_mma"): 0 = always use the FFMA kernel
+// test/tuning hook (bvg_set_tuning "amp_mma"): 0 = never, 1 = where it measured faster than the FFMA2
+// kernel on B200 (profiles/r01_amp_ab.txt: BF16 -> BF16 with C >= 192), 2 = wherever it is supported
+int amp_mma_enable = 1;
 
-// True when the tensor-core kernel takes this descriptor: F32 -> SPLIT (fp32 path) and
-// BF16 -> BF16 (bf16 path) with C a multiple of 8.  Everything else stays on amp_kernel.cu.
+// The tensor-core kernel takes F32 -> SPLIT (fp32 path) and BF16 -> BF16 (bf16 path) with C a multiple
+// of 8.  Everything else stays on amp_kernel.cu.
 bool amp_mma_supported(const bvg_amp_desc* d) {
   if (!amp_mma_enable) return false;
   if (d->C % 8 != 0) return false;
   const bool f32_split = d->x.dtype == BVG_F32 && d->y.dtype == BVG_SPLIT;
   const bool bf_bf = d->x.dtype == BVG_BF16 && d->y.dtype == BVG_BF16;
   if (!f32_split && !bf_bf) return false;
+  if (amp_mma_enable == 1 && !(bf_bf && d->C >= 192)) return false;
   if (((uintptr_t)d->x.d_ptr & 15) || ((uintptr_t)d->y.d_ptr & 15) || (d->y.d_lo && ((uintptr_t)d->y.d_lo & 15))) return false;
   return true;
 }

@@ -28,6 +28,7 @@ int conv_simt_forward(const bvg_conv_desc* d, cudaStream_t st);
 int conv_umma_forward(const bvg_conv_desc* d, cudaStream_t st);
 int post_forward(const bvg_post_desc* d, cudaStream_t st);
 int pack_mel(const bvg_pack_desc* d, cudaStream_t st);
+int tail_forward(const bvg_tail_desc* d, cudaStream_t st);
 int convert(const bvg_tensor* src, const bvg_tensor* dst, size_t n, cudaStream_t st);
 int conv_geometry(const bvg_conv_geom* g, bvg_conv_weights* w);
 size_t conv_plane_elems(const bvg_conv_weights* w);
@@ -106,6 +107,7 @@ int bvg_amp_fwd(const bvg_amp_desc* d, void* stream) { return bvg::amp_forward(d
 int bvg_conv_fwd(const bvg_conv_desc* d, void* stream) { return bvg::conv_forward(d, (cudaStream_t)stream); }
 int bvg_post_fwd(const bvg_post_desc* d, void* stream) { return bvg::post_forward(d, (cudaStream_t)stream); }
 int bvg_pack_mel(const bvg_pack_desc* d, void* stream) { return bvg::pack_mel(d, (cudaStream_t)stream); }
+int bvg_tail_fwd(const bvg_tail_desc* d, void* stream) { return bvg::tail_forward(d, (cudaStream_t)stream); }
 int bvg_convert(const bvg_tensor* src, const bvg_tensor* dst, size_t n, void* stream) {
   return bvg::convert(src, dst, n, (cudaStream_t)stream);
 }

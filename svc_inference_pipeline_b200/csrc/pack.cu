@@ -243,14 +243,21 @@ int pack_post_weights(const float* d_v, const float* d_g, int cin, int ksize, fl
 
 // ---- mel head: [B, C, T] float -> channels-last [B, T, c_pad] ------------------------------------
 template <int OUT_MODE>
-__global__ void pack_mel_kernel(const float* __restrict__ mel, void* out, void* out_lo, int C, int T, int c_pad) {
+__global__ void pack_mel_kernel(const float* __restrict__ mel, void* out, void* out_lo, int C, int T, int c_pad, const float* __restrict__ range,
+                                const float* __restrict__ mn) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
   for (int i = ty; i < 32; i += 8) {
     const int c = c0 + i, t = t0 + tx;
-    tile[i][tx] = (c < C && t < T) ? mel[((long long)b * C + c) * T + t] : 0.f;
+    float v = 0.f;
+    if (c < C && t < T) {
+      v = mel[((long long)b * C + c) * T + t];
+      // fused denormalize_mel_channel: ((mel + 1) / 2) * range + min, each operation rounded to fp32
+      if (range) v = __fadd_rn(__fmul_rn(__fmul_rn(__fadd_rn(v, 1.0f), 0.5f), range[c]), mn[c]);
+    }
+    tile[i][tx] = v;
   }
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
@@ -275,13 +282,14 @@ int pack_mel(const bvg_pack_desc* d, cudaStream_t st) {
   BVG_REQUIRE(d->B > 0 && d->C > 0 && d->T > 0 && d->c_pad >= d->C, "pack_mel: bad shape");
   BVG_REQUIRE(d->out.dtype != BVG_SPLIT || d->out.d_lo, "pack_mel: SPLIT output needs a lo plane");
   BVG_REQUIRE(d->B <= 65535, "pack_mel: batch too large");
+  BVG_REQUIRE((d->d_range == nullptr) == (d->d_min == nullptr), "pack_mel: d_range and d_min go together");
   dim3 grid(ceil_div(d->T, 32), ceil_div(d->c_pad, 32), d->B), block(32, 8);
   if (d->out.dtype == BVG_F32)
-    pack_mel_kernel<BVG_F32><<<grid, block, 0, st>>>(d->d_mel, d->out.d_ptr, nullptr, d->C, d->T, d->c_pad);
+    pack_mel_kernel<BVG_F32><<<grid, block, 0, st>>>(d->d_mel, d->out.d_ptr, nullptr, d->C, d->T, d->c_pad, d->d_range, d->d_min);
   else if (d->out.dtype == BVG_BF16)
-    pack_mel_kernel<BVG_BF16><<<grid, block, 0, st>>>(d->d_mel, d->out.d_ptr, nullptr, d->C, d->T, d->c_pad);
+    pack_mel_kernel<BVG_BF16><<<grid, block, 0, st>>>(d->d_mel, d->out.d_ptr, nullptr, d->C, d->T, d->c_pad, d->d_range, d->d_min);
   else if (d->out.dtype == BVG_SPLIT)
-    pack_mel_kernel<BVG_SPLIT><<<grid, block, 0, st>>>(d->d_mel, d->out.d_ptr, d->out.d_lo, d->C, d->T, d->c_pad);
+    pack_mel_kernel<BVG_SPLIT><<<grid, block, 0, st>>>(d->d_mel, d->out.d_ptr, d->out.d_lo, d->C, d->T, d->c_pad, d->d_range, d->d_min);
   else
     BVG_REQUIRE(false, "pack_mel: bad dtype");
   BVG_CHECK_CUDA(cudaGetLastError());

@@ -70,4 +70,75 @@ int post_forward(const bvg_post_desc* d, cudaStream_t st) {
   return BVG_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Waveform tail: fade-out, peak normalisation, silence padding, PCM16 (see bvg_tail_desc).
+// torch.linspace(1, 0, N) in fp32 (ATen RangeFactories: step = (end - start) / (N - 1); the first
+// half counts up from start, the second half counts down from end):
+//   i < N / 2 : 1 + step * i        else : 0 - step * (N - 1 - i)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fade_weight(int i, int n) {
+  if (n == 1) return 1.0f;
+  const float step = __fdiv_rn(-1.0f, (float)(n - 1));
+  return i < n / 2 ? __fadd_rn(1.0f, __fmul_rn(step, (float)i)) : __fsub_rn(0.0f, __fmul_rn(step, (float)(n - 1 - i)));
+}
+
+__device__ __forceinline__ float faded(const float* __restrict__ w, long long b, int i, int L, int fade_len) {
+  float v = __ldg(w + b * L + i);
+  const int k = i - (L - fade_len);
+  if (k >= 0) v = __fmul_rn(v, fade_weight(k, fade_len));
+  return v;
+}
+
+__global__ void __launch_bounds__(256) tail_peak_kernel(const float* __restrict__ w, float* __restrict__ peak, int L, int fade_len, int chunks) {
+  const int b = blockIdx.x / chunks, c = blockIdx.x % chunks;
+  const long long per = ((long long)L + chunks - 1) / chunks;
+  const long long i0 = c * per, i1 = min((long long)L, i0 + per);
+  float m = 0.f;
+  for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) m = fmaxf(m, fabsf(faded(w, b, (int)i, L, fade_len)));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; ++k) m = fmaxf(m, red[k]);
+    atomicMax(reinterpret_cast<unsigned int*>(peak) + b, __float_as_uint(m));  // m >= 0: uint order == float order
+  }
+}
+
+__global__ void __launch_bounds__(256) tail_pcm_kernel(const float* __restrict__ w, const float* __restrict__ peak, int16_t* __restrict__ pcm, int L,
+                                                       int fade_len, int silence, float volume_peak, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int Lo = L + 2 * silence;
+  const long long b = idx / Lo;
+  const int i = (int)(idx % Lo) - silence;
+  float v = 0.f;
+  if (i >= 0 && i < L) {
+    v = faded(w, b, i, L, fade_len);
+    if (volume_peak > 0.f) {
+      const float pk = peak[b];
+      v = pk > 0.f ? __fmul_rn(v, __fdiv_rn(volume_peak, pk)) : 0.f;  // waveform * (volume_peak / max |waveform|)
+    }
+  }
+  const float q = rintf(__fmul_rn(v, 32768.0f));
+  pcm[idx] = (int16_t)fminf(fmaxf(q, -32768.0f), 32767.0f);
+}
+
+int tail_forward(const bvg_tail_desc* d, cudaStream_t st) {
+  BVG_REQUIRE(d && d->d_wave && d->d_pcm && d->d_peak, "tail: null pointer");
+  BVG_REQUIRE(d->B > 0 && d->L > 0 && d->fade_len >= 0 && d->silence >= 0, "tail: bad shape");
+  BVG_REQUIRE(d->fade_len <= d->L, "tail: fade of %d samples does not fit a %d-sample waveform (fewer than 20 frames)", d->fade_len, d->L);
+  BVG_CHECK_CUDA(cudaMemsetAsync(d->d_peak, 0, sizeof(float) * d->B, st));
+  int chunks = 1;
+  while (chunks < 1024 && (long long)d->L / (chunks * 2) >= 4096) chunks *= 2;
+  tail_peak_kernel<<<(unsigned)(d->B * chunks), 256, 0, st>>>(d->d_wave, d->d_peak, d->L, d->fade_len, chunks);
+  BVG_CHECK_CUDA(cudaGetLastError());
+  const long long total = (long long)d->B * (d->L + 2ll * d->silence);
+  const long long blocks = ceil_div_ll(total, 256);
+  BVG_REQUIRE(blocks < (1ll << 31), "tail: grid too large");
+  tail_pcm_kernel<<<(unsigned)blocks, 256, 0, st>>>(d->d_wave, d->d_peak, d->d_pcm, d->L, d->fade_len, d->silence, d->volume_peak, total);
+  BVG_CHECK_CUDA(cudaGetLastError());
+  return BVG_OK;
+}
+
 }  // namespace bvg

@@ -250,6 +250,7 @@ class Generator(nn.Module):
         self._programs: "OrderedDict[tuple, _Program]" = OrderedDict()
         self.max_cached_programs = 4
         self.use_cuda_graph = False
+        self._mel_denorm = None  # (range, min) device tensors when forward() takes mels normalised to [-1, 1]
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
 
     # -- nn.Module plumbing -------------------------------------------------------------------
@@ -267,6 +268,26 @@ class Generator(nn.Module):
         if precision != self.precision:
             self.precision = precision
             self._invalidate()
+        return self
+
+    def set_mel_denorm(self, mel_min=None, mel_max=None):
+        """Fuse the reference's ``denormalize_mel_channel`` (``utils/acoustic_feature_extraction.py:83-97``,
+        called by ``infer.py:80`` between the acoustic model and the vocoder) into the head kernel:
+        afterwards ``forward`` takes the acoustic model's mel normalised to [-1, 1] and computes
+        ``(mel + 1) / 2 * (mel_max - mel_min + 1e-12) + mel_min`` per channel on the fly (same fp32
+        operation order as the reference's numpy expression).  ``None`` switches the fusion off."""
+        if mel_min is None or mel_max is None:
+            self._mel_denorm = None
+        else:
+            import numpy as np
+
+            mn = np.asarray(mel_min, dtype=np.float32).reshape(-1)
+            mx = np.asarray(mel_max, dtype=np.float32).reshape(-1)
+            if mn.shape != (self.cfg.input_dim,) or mx.shape != mn.shape:
+                raise ValueError(f"mel_min / mel_max must have {self.cfg.input_dim} entries")
+            rng = (mx - mn + np.float32(1e-12)).astype(np.float32)  # float32 array + python float stays float32
+            self._mel_denorm = (torch.from_numpy(rng), torch.from_numpy(mn))
+        self._programs.clear()
         return self
 
     def remove_weight_norm(self):
@@ -417,6 +438,10 @@ class Generator(nn.Module):
         op.u.pack.d_mel = mel_in.data_ptr()
         op.u.pack.out = melp.tensor()
         op.u.pack.B, op.u.pack.C, op.u.pack.T, op.u.pack.c_pad = B, cfg.input_dim, T, pre.x_pitch
+        if self._mel_denorm is not None:
+            rng, mn = (t.to(dev) for t in self._mel_denorm)
+            keep += [rng, mn]
+            op.u.pack.d_range, op.u.pack.d_min = rng.data_ptr(), mn.data_ptr()
         ops.append(op)
         conv_op("conv_pre", melp, h, B, T)
 

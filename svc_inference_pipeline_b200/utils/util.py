@@ -16,7 +16,7 @@ from __future__ import annotations
 import json
 import os
 
-__all__ = ["JsonHParams", "load_config", "loads_json5_subset", "override_config"]
+__all__ = ["JsonHParams", "load_config", "loads_json5_subset", "override_config", "save_audio"]
 
 
 def _strip_json5(text: str) -> str:
@@ -146,3 +146,31 @@ class JsonHParams:
 
 def load_config(config_fn: str) -> JsonHParams:
     return JsonHParams(**_load_config_dict(config_fn))
+
+
+def save_audio(path, waveform, fs, add_silence=True, turn_up=True, volume_peak=0.9):
+    """Reference ``utils/util.py:20-37``: peak-normalise to ``volume_peak``, pad ``fs // 20`` samples of
+    silence on each side, write 16-bit PCM.  ``waveform`` is either the float array
+    ``synthesis_audios`` returns (processed here on the host like the reference does) or the
+    ``int16`` array ``synthesis_pcm16`` returns (already normalised, padded and quantised on the GPU:
+    written as is).  The reference encodes with ``torchaudio.save``; this writes the same container
+    with the stdlib ``wave`` module (no torchcodec / sox dependency)."""
+    import wave
+
+    import numpy as np
+
+    w = np.asarray(waveform)
+    if w.dtype != np.int16:
+        w = w.astype(np.float32)
+        if turn_up:
+            ratio = volume_peak / max(w.max(), abs(w.min()))
+            w = w * np.float32(ratio)
+        if add_silence:
+            silence = np.zeros((fs // 20,), dtype=w.dtype)
+            w = np.concatenate([silence, w, silence])
+        w = np.clip(np.rint(w * np.float32(32768.0)), -32768, 32767).astype(np.int16)
+    with wave.open(path, "wb") as f:
+        f.setnchannels(1)
+        f.setsampwidth(2)
+        f.setframerate(int(fs))
+        f.writeframes(np.ascontiguousarray(w.reshape(-1)).tobytes())

@@ -192,3 +192,52 @@ def test_vocode_long_matches_full(repo_model):
     # distributed entry point degenerates to the same result without a process group
     out2 = S.vocode_long_distributed(repo_model, mel, 256, chunk_frames=256)
     assert (out2 - full).abs().max().item() < 5e-6
+
+
+# ------------------------------------------------------------------------------------------
+# the host steps either side of the vocoder, fused on the device
+# ------------------------------------------------------------------------------------------
+def test_fused_mel_denormalisation(repo_model):
+    """Generator.set_mel_denorm: forward(normalised mel) == forward(denormalize_mel_channel(mel)) bit for
+    bit (the head kernel applies the reference's fp32 expression while it transposes)."""
+    from svc_inference_pipeline_b200.utils.acoustic_feature_extraction import denormalize_mel_channel, load_mel_min_max
+
+    mel_min, mel_max = load_mel_min_max()
+    rng = np.random.default_rng(21)
+    norm = rng.uniform(-1, 1, size=(2, 100, 37)).astype(np.float32)
+    den = np.stack([denormalize_mel_channel(torch.from_numpy(m)).numpy() for m in norm])
+    np.testing.assert_array_equal(den, O.denormalize_mel_channel(norm, mel_min, mel_max))
+    y_host = repo_model(torch.from_numpy(den).to(DEV)).cpu().numpy()
+    try:
+        repo_model.set_mel_denorm(mel_min, mel_max)
+        y_fused = repo_model(torch.from_numpy(norm).to(DEV)).cpu().numpy()
+    finally:
+        repo_model.set_mel_denorm(None, None)
+    np.testing.assert_array_equal(y_fused, y_host)
+    np.testing.assert_array_equal(repo_model(torch.from_numpy(den).to(DEV)).cpu().numpy(), y_host)  # fusion is off again
+
+
+@pytest.mark.parametrize("add_silence,turn_up", [(True, True), (False, True), (True, False)])
+def test_fused_pcm16_tail(repo_model, add_silence, turn_up):
+    """synthesis_pcm16 (fade-out + peak normalisation + silence + int16, two kernels) equals the oracle's
+    restatement of synthesis_audios + save_audio applied to the same generator output, bit for bit, for a
+    single mel and for a batch (every item normalised by its own peak)."""
+    from svc_inference_pipeline_b200.modules.bigvgan_inference import synthesis_audios, synthesis_pcm16
+    from svc_inference_pipeline_b200.utils import synth
+    from svc_inference_pipeline_b200.utils.util import JsonHParams
+
+    cfg = JsonHParams(hop_length=256, fs=24000)
+    mels = torch.from_numpy(synth.synthetic_mel(3, 100, 45, seed=5))
+    wave = repo_model(mels.to(DEV)).cpu().numpy()[:, 0]
+    ref = np.stack([O.synthesis_pcm16(w, 256, 24000, add_silence=add_silence, turn_up=turn_up) for w in wave])
+    got = synthesis_pcm16(repo_model, mels, cfg, add_silence=add_silence, turn_up=turn_up)
+    assert got.dtype == np.int16 and got.shape == ref.shape
+    np.testing.assert_array_equal(got, ref)
+    one = synthesis_pcm16(repo_model, mels[1], cfg, add_silence=add_silence, turn_up=turn_up)
+    np.testing.assert_array_equal(one, ref[1])
+    # and the float path of the reference surface agrees with it to one LSB (torch.linspace's SIMD ramp)
+    audio = synthesis_audios(repo_model, mels[1], cfg)
+    host = O.synthesis_pcm16(wave[1], 256, 24000, add_silence=False, turn_up=False)
+    assert np.abs(np.rint(audio * 32768.0) - host).max() <= 1
+    with pytest.raises(RuntimeError):
+        synthesis_pcm16(repo_model, mels[0, :, :19], cfg)

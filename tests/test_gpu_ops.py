@@ -187,9 +187,10 @@ def test_amp_mma_vs_oracle(ops, shape, mode, fast_sin):
     x_seen = bf16_round(x) if in_dt == L.BF16 else x
     ref = O.activation1d(x_seen.astype(np.float64), alpha.astype(np.float64), beta.astype(np.float64), True, f.astype(np.float64), f.astype(np.float64))
     scale = np.abs(ref).max()
-    y = cf(_ops.activation1d(cl(x), a, invb, f, f, in_dtype=in_dt, out_dtype=out_dt, fast_sin=fast_sin))
-    L.set_tuning("amp_mma", 0)
     try:
+        L.set_tuning("amp_mma", 2)  # force the tensor-core kernel for every supported shape
+        y = cf(_ops.activation1d(cl(x), a, invb, f, f, in_dtype=in_dt, out_dtype=out_dt, fast_sin=fast_sin))
+        L.set_tuning("amp_mma", 0)
         y_ffma = cf(_ops.activation1d(cl(x), a, invb, f, f, in_dtype=in_dt, out_dtype=out_dt, fast_sin=fast_sin))
     finally:
         L.set_tuning("amp_mma", 1)

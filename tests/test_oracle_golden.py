@@ -167,3 +167,73 @@ def test_torch_cpu_port_matches_goldens(golden):
     tsd = {k: torch.from_numpy(v) for k, v in synth.synthetic_state_dict(REPO, seed=0).items()}
     y = P.generator_forward(tsd, REPO, torch.from_numpy(g["logmel_mel"])).numpy()
     assert np.abs(y - g["logmel_y"]).max() < 2e-6
+
+
+def test_linspace_restates_torch():
+    """The fade-out ramp: the oracle's scalar restatement of torch.linspace(1, 0, n) equals torch's own
+    output up to one ulp (torch's vectorised CPU path depends on the host SIMD width), exactly for
+    short ramps, and has the reference's end points."""
+    import torch
+
+    for n in (1, 2, 3, 7, 20, 256, 5120, 20 * 512):
+        ours = O.linspace_1_0(n)
+        ref = torch.linspace(1, 0, steps=n).numpy()
+        assert ours[0] == 1.0 and (n == 1 or ours[-1] == 0.0)
+        assert np.abs(ours - ref).max() <= 2**-23
+        if n <= 20:
+            np.testing.assert_array_equal(ours, ref)
+
+
+def test_denormalize_mel_channel_matches_numpy_expression():
+    """denormalize_mel_channel against the reference's literal numpy expression
+    (utils/acoustic_feature_extraction.py:93) on the reference's own mel_min / mel_max statistics."""
+    import os
+
+    d = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "svc_inference_pipeline_b200", "config", "mel_range.npz"))
+    mel_min, mel_max = d["mel_min"], d["mel_max"]
+    rng = np.random.default_rng(3)
+    mel = rng.uniform(-1, 1, size=(100, 57)).astype(np.float32)
+    ZERO = 1e-12
+    ref = (mel + 1) / 2 * (np.expand_dims(mel_max, -1) - np.expand_dims(mel_min, -1) + ZERO) + np.expand_dims(mel_min, -1)
+    got = O.denormalize_mel_channel(mel, mel_min, mel_max)
+    assert ref.dtype == np.float32
+    np.testing.assert_array_equal(got, ref)
+    from svc_inference_pipeline_b200.utils.acoustic_feature_extraction import denormalize_mel_channel
+    import torch
+
+    np.testing.assert_array_equal(denormalize_mel_channel(torch.from_numpy(mel)).numpy(), ref)
+
+
+def test_synthesis_pcm16_oracle_vs_reference_steps(tmp_path):
+    """The fused tail restated in the oracle equals the reference's host sequence -- synthesis_audios'
+    fade (torch.linspace) then save_audio's numpy arithmetic -- within one PCM LSB, and
+    utils.util.save_audio writes that PCM into a readable 16-bit WAV."""
+    import wave
+
+    import torch
+
+    from svc_inference_pipeline_b200.utils.util import save_audio
+
+    rng = np.random.default_rng(4)
+    hop, fs, frames = 256, 24000, 41
+    audio = (rng.standard_normal(frames * hop) * 0.2).astype(np.float32)
+    pcm = O.synthesis_pcm16(audio, hop, fs)
+    a = torch.from_numpy(audio.copy())
+    a[-20 * hop:] *= torch.linspace(1, 0, steps=20 * hop)
+    w = a.numpy()
+    ratio = 0.9 / max(w.max(), abs(w.min()))
+    w = w * ratio
+    sil = np.zeros((fs // 20,), dtype=w.dtype)
+    w = np.concatenate([sil, w, sil])
+    ref = np.clip(np.rint(w.astype(np.float64) * 32768.0), -32768, 32767).astype(np.int16)
+    assert pcm.shape == ref.shape == (frames * hop + 2 * (fs // 20),)
+    assert np.abs(pcm.astype(np.int32) - ref.astype(np.int32)).max() <= 1
+    assert np.abs(pcm).max() in (29491, 29492)  # 0.9 * 32768
+    path = str(tmp_path / "x.wav")
+    save_audio(path, pcm, fs)
+    with wave.open(path) as f:
+        assert (f.getframerate(), f.getsampwidth(), f.getnchannels(), f.getnframes()) == (fs, 2, 1, pcm.size)
+        np.testing.assert_array_equal(np.frombuffer(f.readframes(pcm.size), dtype=np.int16), pcm)
+    save_audio(path, audio, fs)  # float input: processed on the host like the reference
+    with wave.open(path) as f:
+        assert f.getnframes() == audio.size + 2 * (fs // 20)

@@ -1,12 +1,17 @@
 #!/bin/bash
-# One gpurun call: plain run, ncu launch list of one forward, and --set full captures of three kernels
-# (wide conv, narrow conv, AMP) of the fp32 bench shape.  Usage: tools/gpu_ncu_round.sh <tag>
+# One gpurun call: plain run, ncu launch list (time + DRAM bytes per launch) of one forward of the
+# bench shape for both precisions, and --set full captures of three kernels of the fp32 path
+# (wide conv, narrow conv, Activation1d).  Usage: tools/gpu_ncu_round.sh <tag>
 set -u
-TAG=${1:-v5}
+TAG=${1:-v7}
 OUT=gpurun_out
-python tools/ncu_target.py fp32 > $OUT/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -20 $OUT/plain_$TAG.log; exit 1; }
-ncu --metrics gpu__time_duration.sum --clock-control none -s 227 -c 240 --csv --log-file $OUT/launches_fp32_$TAG.csv python tools/ncu_target.py fp32 > $OUT/ncu_l_$TAG.log 2>&1
-echo "launch list rc=$?"
+M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
+for P in fp32 bf16; do
+  python tools/ncu_target.py $P > $OUT/plain_${P}_$TAG.log 2>&1 || { echo "plain run failed ($P)"; tail -20 $OUT/plain_${P}_$TAG.log; exit 1; }
+  # launches 0..(n-1) are the warm-up forward (+ weight packing); the second forward is the last 235 launches
+  ncu --metrics $M --clock-control none --csv --log-file $OUT/launches_${P}_$TAG.csv python tools/ncu_target.py $P > $OUT/ncu_l_${P}_$TAG.log 2>&1
+  echo "launch list $P rc=$?"
+done
 # second forward starts at conv_umma launch 115 / amp launch 109
 ncu --set full --clock-control none --import-source on -k regex:conv_umma -s 129 -c 1 -o $OUT/prof_conv_s0k11_$TAG -f python tools/ncu_target.py fp32 > $OUT/ncu_a_$TAG.log 2>&1
 echo "wide conv rc=$?"
@@ -14,4 +19,4 @@ ncu --set full --clock-control none --import-source on -k regex:conv_umma -s 224
 echo "narrow conv rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:amp_kernel -s 127 -c 1 -o $OUT/prof_amp_s1_$TAG -f python tools/ncu_target.py fp32 > $OUT/ncu_c_$TAG.log 2>&1
 echo "amp rc=$?"
-ls -la $OUT
+ls -la $OUT | tail -12
