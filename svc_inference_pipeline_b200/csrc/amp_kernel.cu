@@ -336,8 +336,11 @@ __device__ __forceinline__ void amp_block6_p2(const AmpParams& p, const P2 (&xa)
   }
 }
 
+#ifndef BVG_AMP_MINB
+#define BVG_AMP_MINB 8  // 64 registers: measured best on B200 (4 or 6 resident CTAs: 3-5 % slower)
+#endif
 template <bool IN_BF16, int OUT_MODE, bool FAST_SIN>
-__global__ void __launch_bounds__(128) amp_kernel_p2(const __grid_constant__ AmpParams p) {
+__global__ void __launch_bounds__(128, BVG_AMP_MINB) amp_kernel_p2(const __grid_constant__ AmpParams p) {
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= p.total_threads) return;
   const int cg = (int)(tid % p.CG);
