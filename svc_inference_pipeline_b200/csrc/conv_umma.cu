@@ -36,7 +36,7 @@ constexpr int UM_BM = 128;          // rows per M block (TMEM lanes)
 constexpr int UM_KB = 64;           // channels per K slice (one 128-byte swizzle row of bf16)
 constexpr int UM_EPI_WARPS = 8;     // two warps per TMEM lane quarter
 constexpr int UM_THREADS = 128 + 32 * UM_EPI_WARPS;
-constexpr int UM_A_STAGES = 2;
+constexpr int UM_MAX_A_STAGES = 4;   // activation super-tile stages (2..4, chosen per launch)
 constexpr int UM_MAX_B_STAGES = 8;
 constexpr int UM_MAX_T_STAGES = 4;
 constexpr int UM_MAX_MB = 8;
@@ -59,6 +59,7 @@ struct UmmaParams {
   int a_box_rows, a_boxes;  // the A super-tile is loaded as a_boxes TMA boxes of a_box_rows rows
   int col_stride;       // TMEM columns per accumulator (n_tile rounded up to 32)
   int t_stages;         // accumulator stages (each mb * col_stride columns)
+  int a_stages;
   int b_stages;
   int tap_group;        // taps per weight stage (one TMA box of tap_group * n_tile rows)
   int a_stage_bytes;    // all planes
@@ -254,16 +255,16 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
   // carve-up: [A stages][B stages][epilogue staging][barriers][tmem ptr]; base rounded up to 1024 B
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
-  const uint32_t b_base = a_base + UM_A_STAGES * p.a_stage_bytes;
+  const uint32_t b_base = a_base + p.a_stages * p.a_stage_bytes;
   const uint32_t stg_base = b_base + p.b_stages * p.b_stage_bytes;
   const uint32_t bar_base = stg_base + UM_STAGING_BYTES;
   auto a_full = [&](int s) { return bar_base + 8u * s; };
-  auto a_empty = [&](int s) { return bar_base + 8u * (UM_A_STAGES + s); };
-  auto b_full = [&](int s) { return bar_base + 8u * (2 * UM_A_STAGES + s); };
-  auto b_empty = [&](int s) { return bar_base + 8u * (2 * UM_A_STAGES + UM_MAX_B_STAGES + s); };
-  auto t_full = [&](int s) { return bar_base + 8u * (2 * UM_A_STAGES + 2 * UM_MAX_B_STAGES + s); };
-  auto t_empty = [&](int s) { return bar_base + 8u * (2 * UM_A_STAGES + 2 * UM_MAX_B_STAGES + UM_MAX_T_STAGES + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * UM_A_STAGES + 2 * UM_MAX_B_STAGES + 2 * UM_MAX_T_STAGES);
+  auto a_empty = [&](int s) { return bar_base + 8u * (UM_MAX_A_STAGES + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * UM_MAX_A_STAGES + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * UM_MAX_A_STAGES + UM_MAX_B_STAGES + s); };
+  auto t_full = [&](int s) { return bar_base + 8u * (2 * UM_MAX_A_STAGES + 2 * UM_MAX_B_STAGES + s); };
+  auto t_empty = [&](int s) { return bar_base + 8u * (2 * UM_MAX_A_STAGES + 2 * UM_MAX_B_STAGES + UM_MAX_T_STAGES + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * UM_MAX_A_STAGES + 2 * UM_MAX_B_STAGES + 2 * UM_MAX_T_STAGES);
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));  // generic pointer to smem_base
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
     }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < UM_A_STAGES; ++s) {
+    for (int s = 0; s < p.a_stages; ++s) {
       ptx::mbar_init(a_full(s), 1);
       ptx::mbar_init(a_empty(s), 1);
     }
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
                                  row0 + bx * p.a_box_rows, b);
           }
           __syncwarp();
-          if (++sa == UM_A_STAGES) { sa = 0; pa ^= 1; }
+          if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
           // weights: one box of tap_group consecutive taps per (group, plane); rows past the last
           // tap of this N tile belong to the next tile (or are zero-filled past the end) and are unused
           for (int g0 = 0; g0 < ntaps; g0 += p.tap_group) {
@@ -413,7 +414,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
           }
           if (ptx::elect_one()) ptx::umma_commit(a_empty(sa));
           __syncwarp();
-          if (++sa == UM_A_STAGES) { sa = 0; pa ^= 1; }
+          if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
         }
         if (ptx::elect_one()) ptx::umma_commit(t_full(as));  // accumulators complete -> epilogue
         __syncwarp();
@@ -645,20 +646,21 @@ int umma_mb = 0;         // tuning/test hook: force M blocks per tile (0 = choos
 int umma_wide_mb2 = 0;   // tuning/test hook: allow mb = 2 with a single TMEM stage for 256-column tiles
 int umma_max_ctas = 0;   // tuning/test hook: cap the persistent grid
 int umma_tap_group = 0;  // tuning/test hook: taps per weight stage (0 = choose)
+int umma_a_stages = 0;   // tuning/test hook: activation stages (0 = choose)
 
-static const int kBarBytes = 8 * (2 * UM_A_STAGES + 2 * UM_MAX_B_STAGES + 2 * UM_MAX_T_STAGES) + 16;
+static const int kBarBytes = 8 * (2 * UM_MAX_A_STAGES + 2 * UM_MAX_B_STAGES + 2 * UM_MAX_T_STAGES) + 16;
 
 // shared-memory plan for a given number of M blocks: picks the taps per weight stage (narrow N
 // tiles group several taps into one TMA box / one barrier round trip) and returns the number of
 // weight stages that fit
-static int plan_smem(int mb, int max_span, int planes, int n_tile, int max_taps, int* box_rows, int* boxes, int* tap_group) {
+static int plan_smem(int mb, int a_stages, int max_span, int planes, int n_tile, int max_taps, int* box_rows, int* boxes, int* tap_group) {
   const int rows = mb * UM_BM + max_span;
   const int nb = (rows + 255) / 256;
   const int br = (((rows + nb - 1) / nb) + 7) / 8 * 8;
   *box_rows = br;
   *boxes = nb;
   const int a_stage = nb * br * 128 * planes;
-  const int avail = UM_SMEM_LIMIT - 1024 - kBarBytes - UM_STAGING_BYTES - UM_A_STAGES * a_stage;
+  const int avail = UM_SMEM_LIMIT - 1024 - kBarBytes - UM_STAGING_BYTES - a_stages * a_stage;
   if (avail <= 0) return 0;
   int g = umma_tap_group > 0 ? umma_tap_group : 24 * 1024 / (n_tile * 128);  // ~24 KB per stage
   if (g > 256 / n_tile) g = 256 / n_tile;                                      // TMA box <= 256 rows
@@ -726,7 +728,7 @@ int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out) {
     int br, nb, tg;
     const bool tmem_ok = cand * p.col_stride * 2 <= 512 || (cand == 1) || (umma_wide_mb2 && cand == 2 && cand * p.col_stride <= 512);
     if (!tmem_ok) continue;
-    if (plan_smem(cand, max_span, planes, w->n_tile, max_taps, &br, &nb, &tg) < (cand == 1 ? 2 : 3)) continue;
+    if (plan_smem(cand, 2, max_span, planes, w->n_tile, max_taps, &br, &nb, &tg) < (cand == 1 ? 2 : 3)) continue;
     const long long tiles = (long long)d->B * ceil_div(d->L, cand * UM_BM) * w->n_tiles;
     if (cand > 1 && tiles < 2ll * sms) continue;
     mb = cand;
@@ -740,13 +742,26 @@ int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out) {
   p.total_tiles = (long long)d->B * p.m_tiles_per_item * w->n_tiles;
   p.t_stages = 512 / (mb * p.col_stride);
   if (p.t_stages > UM_MAX_T_STAGES) p.t_stages = UM_MAX_T_STAGES;
-  const int bs = plan_smem(mb, max_span, planes, w->n_tile, max_taps, &p.a_box_rows, &p.a_boxes, &p.tap_group);
+  // activation stages: a tile's MMAs cannot start before its whole super-tile has landed, so when one
+  // tile is short (narrow N: ~2k cycles of MMA) two stages leave the TMA round trip exposed; take as many
+  // (up to 4) as still leave three weight stages
+  int a_stages = 2;
+  for (int cand = UM_MAX_A_STAGES; cand > 2; --cand) {
+    int br, nb, tg;
+    if (umma_a_stages == -1 && p.n_cb <= 2 && plan_smem(mb, cand, max_span, planes, w->n_tile, max_taps, &br, &nb, &tg) >= 3) {
+      a_stages = cand;
+      break;
+    }
+  }
+  if (umma_a_stages >= 2 && umma_a_stages <= UM_MAX_A_STAGES) a_stages = umma_a_stages;
+  p.a_stages = a_stages;
+  const int bs = plan_smem(mb, a_stages, max_span, planes, w->n_tile, max_taps, &p.a_box_rows, &p.a_boxes, &p.tap_group);
   BVG_REQUIRE(bs >= 2, "conv_umma: tile does not fit in shared memory (mb %d, span %d, n_tile %d, planes %d)", mb, max_span, w->n_tile, planes);
   p.b_stages = bs;
   p.a_plane_bytes = p.a_boxes * p.a_box_rows * 128;
   p.a_stage_bytes = p.a_plane_bytes * planes;
   p.b_stage_bytes = p.tap_group * w->n_tile * 128;
-  size_t smem = 1024 + (size_t)UM_A_STAGES * p.a_stage_bytes + (size_t)bs * p.b_stage_bytes + UM_STAGING_BYTES + kBarBytes;
+  size_t smem = 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)bs * p.b_stage_bytes + UM_STAGING_BYTES + kBarBytes;
   // keep one CTA per SM (each allocates all 512 TMEM columns): ask for more than half the SM's smem
   if (smem < 120 * 1024) smem = 120 * 1024;
   BVG_REQUIRE(smem <= (size_t)UM_SMEM_LIMIT, "conv_umma: shared memory plan exceeds the limit");
