@@ -230,6 +230,10 @@ int bvg_program_run(bvg_program* p, void* stream);
  * device time (ms) and launch count per bvg_op_kind (arrays of 4).  Measurement aid for bench.py. */
 int bvg_program_run_timed(bvg_program* p, void* stream, float* ms_by_kind, int32_t* n_by_kind,
                           float* ms_per_op /* optional, n_ops entries */);
+/* Issue n programs with the same op sequence op by op, program k on streams[k].  Each stream keeps its own
+ * order; launching the ops alternately lets one half-batch's tensor-core convolutions (one persistent CTA per
+ * SM, almost no issue slots) share the SMs with the other half-batch's FFMA-bound Activation1d kernels. */
+int bvg_program_run_interleaved(bvg_program* const* progs, void* const* streams, int32_t n);
 int bvg_program_num_launches(const bvg_program* p);
 void bvg_program_destroy(bvg_program* p);
 

@@ -157,6 +157,7 @@ EXPORTS = [
     "bvg_convert",
     "bvg_program_create",
     "bvg_program_run",
+    "bvg_program_run_interleaved",
     "bvg_program_run_timed",
     "bvg_set_tuning",
     "bvg_program_num_launches",
@@ -194,6 +195,7 @@ def lib():
         "bvg_pack_post_weights": [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p],
         "bvg_program_create": [C.POINTER(Op), C.c_int32, C.POINTER(C.c_void_p)],
         "bvg_program_run": [C.c_void_p, C.c_void_p],
+        "bvg_program_run_interleaved": [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32],
         "bvg_program_run_timed": [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_float)],
         "bvg_program_num_launches": [C.c_void_p],
         "bvg_program_destroy": [C.c_void_p],

@@ -336,11 +336,10 @@ __device__ __forceinline__ void amp_block6_p2(const AmpParams& p, const P2 (&xa)
   }
 }
 
-#ifndef BVG_AMP_MINB
-#define BVG_AMP_MINB 8  // 64 registers: measured best on B200 (4 or 6 resident CTAs: 3-5 % slower)
-#endif
+// plain __launch_bounds__(128): ptxas settles at 56-66 registers; forcing 8 resident CTAs (64 registers)
+// spills in the bf16 variants (2.4x slower), allowing 4-6 CTAs' worth of registers is 3-5 % slower (B200)
 template <bool IN_BF16, int OUT_MODE, bool FAST_SIN>
-__global__ void __launch_bounds__(128, BVG_AMP_MINB) amp_kernel_p2(const __grid_constant__ AmpParams p) {
+__global__ void __launch_bounds__(128) amp_kernel_p2(const __grid_constant__ AmpParams p) {
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= p.total_threads) return;
   const int cg = (int)(tid % p.CG);
@@ -387,6 +386,16 @@ template <bool IN_BF16, int OUT_MODE>
 static cudaError_t launch_amp_p2(const AmpParams& p, bool fast, cudaStream_t st) {
   const int threads = 128;
   const long long blocks = ceil_div_ll(p.total_threads, threads);
+  // Same shared-memory carve-out as the convolution kernel (max shared): an SM can only host kernels of
+  // two streams at once when they agree on the L1 / shared split, and this kernel streams through L2 anyway.
+  static bool configured[2] = {false, false};
+  if (!configured[fast ? 1 : 0]) {
+    if (fast)
+      cudaFuncSetAttribute(amp_kernel_p2<IN_BF16, OUT_MODE, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    else
+      cudaFuncSetAttribute(amp_kernel_p2<IN_BF16, OUT_MODE, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    configured[fast ? 1 : 0] = true;
+  }
   if (fast)
     amp_kernel_p2<IN_BF16, OUT_MODE, true><<<(unsigned)blocks, threads, 0, st>>>(p);
   else

@@ -204,6 +204,28 @@ int bvg_program_run(bvg_program* p, void* stream) {
   return BVG_OK;
 }
 
+int bvg_program_run_interleaved(bvg_program* const* progs, void* const* streams, int32_t n) {
+  if (!progs || !streams || n <= 0) {
+    bvg::set_error("program_run_interleaved: bad argument");
+    return BVG_EINVAL;
+  }
+  size_t n_ops = 0;
+  for (int k = 0; k < n; ++k) {
+    if (!progs[k]) {
+      bvg::set_error("program_run_interleaved: null program");
+      return BVG_EINVAL;
+    }
+    if (progs[k]->ops.size() > n_ops) n_ops = progs[k]->ops.size();
+  }
+  for (size_t i = 0; i < n_ops; ++i)
+    for (int k = 0; k < n; ++k) {
+      if (i >= progs[k]->ops.size()) continue;
+      int rc = run_one(progs[k], i, (cudaStream_t)streams[k]);
+      if (rc != BVG_OK) return rc;
+    }
+  return BVG_OK;
+}
+
 int bvg_program_run_timed(bvg_program* p, void* stream, float* ms_by_kind, int32_t* n_by_kind, float* ms_per_op) {
   if (!p || !ms_by_kind || !n_by_kind) {
     bvg::set_error("program_run_timed: bad argument");

@@ -252,8 +252,13 @@ class Generator(nn.Module):
         self.hop = int(math.prod(cfg.upsample_rates))
         self._packed = None
         self._programs: "OrderedDict[tuple, _Program]" = OrderedDict()
-        self.max_cached_programs = 4
+        self.max_cached_programs = 6
         self.use_cuda_graph = False
+        # Two half-batches on two streams, launched op by op in alternation: the tensor-core convolutions of
+        # one half (one persistent CTA per SM, ~6 % of the issue slots) share the SMs with the FFMA-bound
+        # Activation1d kernels of the other half.  Needs >= 2 utterances; results are identical.
+        self.overlap_streams = True
+        self._side_streams = None
         self._mel_denorm = None  # (range, min) device tensors when forward() takes mels normalised to [-1, 1]
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
 
@@ -503,8 +508,9 @@ class Generator(nn.Module):
         prog.labels = labels
         return prog
 
-    def _program(self, B: int, T: int) -> _Program:
-        key = (B, T, self.precision)
+    def _program(self, B: int, T: int, slot: int = -1) -> _Program:
+        # slot >= 0: one of the two half-batch programs of the overlapped forward (own workspace each)
+        key = (B, T, self.precision, slot)
         prog = self._programs.get(key)
         if prog is None:
             with torch.cuda.device(self._device()):
@@ -569,6 +575,8 @@ class Generator(nn.Module):
         B, _, T = x.shape
         if B == 0 or T == 0:
             return torch.empty(B, 1, T * self.hop, dtype=torch.float32, device=dev)
+        if self.overlap_streams and B >= 2 and not self.use_cuda_graph:
+            return self._forward_overlapped(x, dev)
         prog = self._program(B, T)
         with torch.cuda.device(dev):
             prog.mel_in.copy_(x, non_blocking=True)
@@ -585,3 +593,24 @@ class Generator(nn.Module):
             else:
                 prog.run(stream.cuda_stream)
             return prog.out.clone()
+
+    def _forward_overlapped(self, x: torch.Tensor, dev) -> torch.Tensor:
+        B, _, T = x.shape
+        b0 = (B + 1) // 2
+        parts = [(0, b0), (b0, B)]
+        with torch.cuda.device(dev):
+            progs = [self._program(hi - lo, T, slot=k) for k, (lo, hi) in enumerate(parts)]
+            if self._side_streams is None or self._side_streams[0].device != dev:
+                self._side_streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+            cur = torch.cuda.current_stream(dev)
+            for prog, (lo, hi) in zip(progs, parts):
+                prog.mel_in.copy_(x[lo:hi], non_blocking=True)
+            ready = cur.record_event()
+            for st in self._side_streams:
+                st.wait_event(ready)
+            handles = (C.c_void_p * 2)(progs[0].handle, progs[1].handle)
+            streams = (C.c_void_p * 2)(self._side_streams[0].cuda_stream, self._side_streams[1].cuda_stream)
+            L.check(L.lib().bvg_program_run_interleaved(handles, streams, 2), "program_run_interleaved")
+            for st in self._side_streams:
+                cur.wait_event(st.record_event())
+            return torch.cat([progs[0].out, progs[1].out], dim=0)

@@ -241,3 +241,22 @@ def test_fused_pcm16_tail(repo_model, add_silence, turn_up):
     assert np.abs(np.rint(audio * 32768.0) - host).max() <= 1
     with pytest.raises(RuntimeError):
         synthesis_pcm16(repo_model, mels[0, :, :19], cfg)
+
+
+@pytest.mark.parametrize("B", [2, 3, 5])
+def test_overlapped_forward_is_identical(repo_model, B):
+    """Two half-batches on two streams (Generator.overlap_streams, the default for B >= 2) give exactly the
+    waveform of the single-program forward, for even and odd batch sizes, and repeated calls are stable."""
+    from svc_inference_pipeline_b200.utils import synth
+
+    mel = torch.from_numpy(synth.synthetic_mel(B, 100, 53, seed=31)).to(DEV)
+    assert repo_model.overlap_streams
+    y_ov = repo_model(mel)
+    y_ov2 = repo_model(mel)
+    try:
+        repo_model.overlap_streams = False
+        y_plain = repo_model(mel)
+    finally:
+        repo_model.overlap_streams = True
+    assert y_ov.shape == (B, 1, 53 * 256)
+    assert torch.equal(y_ov, y_plain) and torch.equal(y_ov, y_ov2)
