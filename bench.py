@@ -41,6 +41,15 @@ GFLOP_PER_FRAME = 1.8041      # dense-conv FLOPs per mel frame (SURVEY.md sectio
 AMP_ELEMS_PER_FRAME = 614_400  # Activation1d elements per mel frame over the 109 calls
 
 
+def load_traffic(precision, kernel):
+    """DRAM bytes per launch of a kernel class from the committed ncu launch list (None if absent)."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic_v7.json")
+    try:
+        return json.load(open(path))[precision][kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -230,7 +239,8 @@ def main():
         barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     value = world * audio_s_per_step * steps / (ms / 1e3)
-    launches = model.launches_per_forward(B, T) * steps
+    # the overlapped forward issues two half-batch programs (two streams) per step
+    launches = model.launches_per_forward(B, T) * (2 if (model.overlap_streams and B >= 2) else 1) * steps
 
     # ---- e2e: the reference-facing call with host buffers ------------------------------------------
     def e2e_step():
@@ -256,11 +266,15 @@ def main():
     conv_tflops = conv_flops / (prof["conv_ms"] / 1e3) / 1e12
     amp_gbs = amp_bytes / (prof["amp_ms"] / 1e3) / 1e9
     roofline = {"bound": "tensor", "kernel": "conv_umma_kernel (116 launches/step)" if args.precision != "fp32_simt" else "conv_simt_kernel",
-                "achieved": conv_tflops, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": conv_tflops / peaks["tensor"], "traffic": None,
+                "achieved": conv_tflops, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": conv_tflops / peaks["tensor"],
+                "traffic": load_traffic("bf16" if args.precision == "bf16" else "fp32", "conv_umma_kernel"),
+                "issued_tflops": conv_tflops * (3 if args.precision == "fp32" else 1), "issued_frac": conv_tflops * (3 if args.precision == "fp32" else 1) / peaks["tensor"],
                 "peak_source": peaks["src"], "avg_launch_ms": prof["conv_ms"] / max(1, prof["conv_n"]), "share_of_step": prof["conv_ms"] / prof["total_ms"],
-                "note": "algorithmic FLOPs 2*Cin*Cout*K*L per conv (1.8041 GFLOP/frame); the fp32 path issues 3 bf16 MMAs per product, counted once"}
-    roofline_amp = {"bound": "hbm", "kernel": "amp_kernel (109 launches/step)", "achieved": amp_gbs, "peak": peaks["hbm"], "unit": "GB/s",
-                    "frac": amp_gbs / peaks["hbm"], "traffic": None, "avg_launch_ms": prof["amp_ms"] / max(1, prof["amp_n"]),
+                "note": "algorithmic FLOPs 2*Cin*Cout*K*L per conv (1.8041 GFLOP/frame); the fp32 path issues 3 bf16 MMAs per product (hi*hi + lo*hi + hi*lo), "
+                        "counted once in achieved/frac and three times in issued_*; ncu: 98 % tensor-pipe active on the C>=384 layers (profiles/r01_ncu_summary_v7.md); "
+                        "traffic = mean DRAM bytes per launch from the committed ncu launch list"}
+    roofline_amp = {"bound": "hbm", "kernel": "amp_kernel_p2 / amp_mma_kernel (109 launches/step)", "achieved": amp_gbs, "peak": peaks["hbm"], "unit": "GB/s",
+                    "frac": amp_gbs / peaks["hbm"], "traffic": load_traffic("bf16" if args.precision == "bf16" else "fp32", "amp_kernel"), "avg_launch_ms": prof["amp_ms"] / max(1, prof["amp_n"]),
                     "share_of_step": prof["amp_ms"] / prof["total_ms"], "bytes_per_elem": 8 if args.precision != "bf16" else 4}
 
     line = {
@@ -270,6 +284,7 @@ def main():
         "data": "synthetic (log-mel range of the reference's mel_min/max; random-init checkpoint, seed 0)",
         "config": {"workload": WORKLOAD if (B, T) == (BATCH_PER_GPU, FRAMES_PER_ITEM) else f"custom batch {B} x {T} frames", "batch_per_gpu": B, "frames": T,
                    "precision": args.precision, "l2": "activation working set (GBs) far exceeds the 126 MB L2; no flush needed",
+                   "streams": "two half-batches on two CUDA streams per rank, ops launched alternately" if (model.overlap_streams and B >= 2) else "one stream",
                    "parallelism": f"dp{world}: independent utterances per rank" + (", all_gather of waveforms inside the step" if world > 1 else "")},
         "e2e": e2e, "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline, "roofline_amp": roofline_amp,
         "class_ms_per_step": {k: prof[k] for k in ("conv_ms", "amp_ms", "other_ms", "total_ms")},
@@ -295,6 +310,25 @@ def main():
                         "amp_frac": AMP_ELEMS_PER_FRAME * frames * 4 / (bprof["amp_ms"] / 1e3) / 1e9 / peaks["hbm"],
                         "class_ms_per_step": {k: bprof[k] for k in ("conv_ms", "amp_ms", "other_ms", "total_ms")}}
         model.set_precision(args.precision)
+
+    if rank == 0:
+        # configs[0] shape: one utterance of 379 frames (4.04 s) through synthesis_audios, eager and as a CUDA graph
+        from svc_inference_pipeline_b200.modules.bigvgan_inference import synthesis_audios
+        m1 = torch.from_numpy(synth.synthetic_mel(1, 100, 379, seed=1234))[0]
+        lat = {}
+        for graph in (False, True):
+            model.use_cuda_graph = graph
+            for _ in range(3):
+                synthesis_audios(model, m1, cfg)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for _ in range(5):
+                synthesis_audios(model, m1, cfg)
+            lat["cuda_graph_ms" if graph else "eager_ms"] = (time.perf_counter() - t0) / 5 * 1e3
+        model.use_cuda_graph = False
+        lat["audio_s"] = 379 * HOP / FS
+        lat["api"] = "synthesis_audios(model, mel[100,379], cfg): H2D + forward + D2H + fade, wall clock"
+        line["single_utterance_latency"] = lat
 
     if rank == 0 and args.torch_gpu_baseline:
         from oracle import bigvgan_torch_cpu as port
