@@ -393,3 +393,125 @@ def test_post(ops):
     ref = np.tanh(O.conv1d(x.astype(np.float64), w, b.astype(np.float64), 1, 3))[:, 0]
     y = _ops.post(cl(x), *(torch.from_numpy(t).to(DEV) for t in (v, g, b))).cpu().numpy()
     assert np.abs(y - ref).max() < 2e-6
+
+
+# ------------------------------------------------------------------------------------------
+# guard-band checks (compute-sanitizer is closed on this pool): every kernel that masks partial
+# tiles writes into a buffer surrounded by sentinels, which must survive
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kernel", ["mma", "packed", "scalar"])
+@pytest.mark.parametrize("mode", ["f32_split", "bf16_bf16", "f32_f32"])
+def test_amp_guard_bands(ops, kernel, mode):
+    import ctypes as C
+
+    _ops, L = ops
+    if kernel == "mma" and mode == "f32_f32":
+        pytest.skip("the tensor-core kernel does not take F32 -> F32")
+    in_dt, out_dt = {"f32_split": (L.F32, L.SPLIT), "bf16_bf16": (L.BF16, L.BF16), "f32_f32": (L.F32, L.F32)}[mode]
+    G = 4096
+    f = golden_taps()
+    rng = np.random.default_rng(9)
+    for (B, Ch, Ln) in [(2, 24, 61), (1, 40, 130), (3, 8, 7), (1, 112, 257), (2, 48, 64)]:
+        n = B * Ln * Ch
+        x = torch.from_numpy((rng.standard_normal(n) * 1.5).astype(np.float32)).to(DEV)
+        xin = x if in_dt == L.F32 else x.to(torch.bfloat16)
+        odt = torch.float32 if out_dt == L.F32 else torch.bfloat16
+        sent = 12345.0
+        planes = [torch.full((n + 2 * G,), sent, dtype=odt, device=DEV) for _ in range(2 if out_dt == L.SPLIT else 1)]
+        a, invb = snake_params((rng.standard_normal(Ch) * 0.3).astype(np.float32), (rng.standard_normal(Ch) * 0.3).astype(np.float32), True)
+        d = L.AmpDesc()
+        d.x = L.Tensor(xin.data_ptr(), None, in_dt, 0)
+        esz = planes[0].element_size()
+        d.y = L.Tensor(planes[0].data_ptr() + G * esz, (planes[1].data_ptr() + G * esz) if len(planes) > 1 else None, out_dt, 0)
+        d.d_a, d.d_invb = a.data_ptr(), invb.data_ptr()
+        d.taps_up = (C.c_float * 12)(*f.tolist())
+        d.taps_down = (C.c_float * 12)(*f.tolist())
+        d.B, d.L, d.C, d.fast_sin = B, Ln, Ch, 1
+        try:
+            L.set_tuning("amp_mma", 2 if kernel == "mma" else 0)
+            L.set_tuning("amp_packed", 0 if kernel == "scalar" else 1)
+            L.check(L.lib().bvg_amp_fwd(C.byref(d), torch.cuda.current_stream().cuda_stream), "amp_fwd")
+            torch.cuda.synchronize()
+        finally:
+            L.set_tuning("amp_mma", 1)
+            L.set_tuning("amp_packed", 1)
+        for pl in planes:
+            assert bool((pl[:G] == sent).all()) and bool((pl[-G:] == sent).all()), (kernel, mode, B, Ch, Ln)
+            assert bool((pl[G:-G] != sent).all())  # and every element inside was written
+
+
+def test_tail_and_pack_guard_bands(ops):
+    import ctypes as C
+
+    _ops, L = ops
+    G = 1024
+    rng = np.random.default_rng(10)
+    B, Ln, sil, fade = 3, 5000, 37, 640
+    wave = torch.from_numpy((rng.standard_normal(B * Ln) * 0.1).astype(np.float32)).to(DEV)
+    n = B * (Ln + 2 * sil)
+    pcm = torch.full((n + 2 * G,), 777, dtype=torch.int16, device=DEV)
+    peak = torch.full((B + 2,), -1.0, dtype=torch.float32, device=DEV)
+    d = L.TailDesc()
+    d.d_wave, d.d_pcm, d.d_peak = wave.data_ptr(), pcm.data_ptr() + 2 * G, peak.data_ptr() + 4
+    d.B, d.L, d.fade_len, d.silence, d.volume_peak = B, Ln, fade, sil, 0.9
+    L.check(L.lib().bvg_tail_fwd(C.byref(d), torch.cuda.current_stream().cuda_stream), "tail_fwd")
+    torch.cuda.synchronize()
+    assert bool((pcm[:G] == 777).all()) and bool((pcm[-G:] == 777).all())
+    assert float(peak[0]) == -1.0 and float(peak[-1]) == -1.0 and bool((peak[1:-1] > 0).all())
+    got = pcm[G:-G].cpu().numpy().reshape(B, -1)
+    ref = np.stack([O.synthesis_pcm16(w, fade // 20, sil * 20) for w in wave.cpu().numpy().reshape(B, Ln)])
+    np.testing.assert_array_equal(got, ref)
+    # head: [B, C, T] -> [B, T, c_pad] with zero-filled pad channels
+    Bm, Cm, Tm, cpad = 2, 100, 45, 104
+    mel = torch.from_numpy(rng.standard_normal((Bm, Cm, Tm)).astype(np.float32)).to(DEV)
+    out = torch.full((Bm * Tm * cpad + 2 * G,), 5.0, dtype=torch.float32, device=DEV)
+    pd = L.PackDesc()
+    pd.d_mel = mel.data_ptr()
+    pd.out = L.Tensor(out.data_ptr() + 4 * G, None, L.F32, 0)
+    pd.B, pd.C, pd.T, pd.c_pad = Bm, Cm, Tm, cpad
+    L.check(L.lib().bvg_pack_mel(C.byref(pd), torch.cuda.current_stream().cuda_stream), "pack_mel")
+    torch.cuda.synchronize()
+    assert bool((out[:G] == 5.0).all()) and bool((out[-G:] == 5.0).all())
+    body = out[G:-G].reshape(Bm, Tm, cpad)
+    assert torch.equal(body[:, :, :Cm], mel.permute(0, 2, 1)) and bool((body[:, :, Cm:] == 0).all())
+
+
+@pytest.mark.parametrize("backend", ["umma_split", "umma_bf16", "simt"])
+def test_conv_guard_bands(ops, backend):
+    """Convolution epilogues (partial M tiles, N tiles wider than Cout, transposed convs) never write
+    outside [B, L, n_total]."""
+    import ctypes as C
+
+    _ops, L = ops
+    G = 8192
+    rng = np.random.default_rng(12)
+    be = L.SIMT if backend == "simt" else L.UMMA
+    split = backend == "umma_split"
+    x_dt = L.F32 if backend == "simt" else (L.SPLIT if split else L.BF16)
+    for (cin, cout, k, dil, stride, tr, B, Ln) in [(24, 24, 11, 5, 1, False, 2, 301), (48, 48, 7, 3, 1, False, 1, 130), (96, 48, 4, 1, 2, True, 2, 77),
+                                                  (200, 200, 3, 1, 1, False, 1, 257), (16, 8, 8, 1, 4, True, 3, 33)]:
+        shape = (cin, cout, k) if tr else (cout, cin, k)
+        v = torch.from_numpy(rng.standard_normal(shape).astype(np.float32) * 0.1).to(DEV)
+        g = v.flatten(1).norm(dim=1).reshape(-1, 1, 1) * 1.1
+        bias = torch.from_numpy(rng.standard_normal(cout).astype(np.float32)).to(DEV)
+        pad = (k - stride) // 2 if tr else (k * dil - dil) // 2
+        pc = _ops.pack_conv(v, g, bias, transposed=tr, dilation=dil, stride=stride, padding=pad, backend=be, split=split)
+        x = torch.from_numpy(rng.standard_normal((B, Ln, pc.x_pitch)).astype(np.float32)).to(DEV)
+        if pc.x_pitch > cin:
+            x[:, :, cin:] = 0
+        xb = _ops.to_buf(x, x_dt)
+        n = B * Ln * pc.n_total
+        for out_dt in ((L.F32, L.SPLIT) if backend != "umma_bf16" else (L.BF16,)):
+            odt = torch.float32 if out_dt == L.F32 else torch.bfloat16
+            planes = [torch.full((n + 2 * G,), 321.0, dtype=odt, device=DEV) for _ in range(2 if out_dt == L.SPLIT else 1)]
+            esz = planes[0].element_size()
+            d = L.ConvDesc()
+            d.x = xb.tensor()
+            d.out = L.Tensor(planes[0].data_ptr() + G * esz, (planes[1].data_ptr() + G * esz) if len(planes) > 1 else None, out_dt, 0)
+            d.res = d.acc_in = L.Tensor(None, None, L.F32, 0)
+            d.div, d.B, d.L = 1.0, B, Ln
+            d.w = C.pointer(pc.desc)
+            L.check(L.lib().bvg_conv_fwd(C.byref(d), torch.cuda.current_stream().cuda_stream), "conv_fwd")
+            torch.cuda.synchronize()
+            for pl in planes:
+                assert bool((pl[:G] == 321.0).all()) and bool((pl[-G:] == 321.0).all()), (backend, cin, cout, k, out_dt)
