@@ -134,7 +134,10 @@ __global__ void __launch_bounds__(32 * NG) amp_mma_kernel(const __grid_constant_
   constexpr int PLANE = AM_ROWS * PITCH;
   constexpr int STG_PLANE = 8 * 48;   // 8 rows x 16 channels, 48-byte pitch (conflict-free stmatrix)
   constexpr int STG = STG_PLANE * NOUT;
-  __shared__ __align__(16) uint8_t smem[NPL * PLANE + NG * 2 * STG];  // x planes + two staging buffers per warp
+  // bf16 input: two tile buffers filled by cp.async (no staging registers); fp32 input: the (hi, lo) planes of
+  // one tile, written from registers after the split.  Then two output staging buffers per warp.
+  constexpr int XBYTES = 2 * PLANE;
+  __shared__ __align__(16) uint8_t smem[XBYTES + NG * 2 * STG];
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(32 * NG) amp_mma_kernel(const __grid_constant_
   }
   // ldmatrix row address of this lane: matrix j = lane / 8 -> times +8 * (j / 2), channels +8 * (j % 2)
   const uint32_t ld_base = amm::smem_u32(smem) + (uint32_t)(((lane & 7) + 8 * (lane >> 4)) * PITCH + 32 * g + 16 * ((lane >> 3) & 1));
-  uint8_t* const stg = smem + NPL * PLANE + g * 2 * STG;
+  uint8_t* const stg = smem + XBYTES + g * 2 * STG;
   // stmatrix row address: matrix j = lane / 8 -> plane j / 2, channels +8 * (j % 2); row lane % 8
   const uint32_t st_addr = amm::smem_u32(stg) + (uint32_t)((lane >> 4) * STG_PLANE + (lane & 7) * 48 + ((lane >> 3) & 1) * 16);
   // read-back: lane -> plane lane / 16, row (lane % 16) / 2, channel half lane % 2
@@ -279,9 +282,9 @@ __global__ void __launch_bounds__(32 * NG) amp_mma_kernel(const __grid_constant_
   SFrag fa, fb;  // ping-pong: fa holds the s-block a staged tile starts from
 
   // one staged tile: z-tiles mt .. mt + AM_NB - 1 (EDGE: clamps, partial last tile, row predicates)
-  auto run_tile = [&](auto edge_tag, int mt) {
+  auto run_tile = [&](auto edge_tag, int mt, uint32_t xoff) {
     constexpr bool EDGE = decltype(edge_tag)::value;
-    uint32_t addr = ld_base + 8 * PITCH;                        // s-block mt + 1 starts at staged row 8
+    uint32_t addr = ld_base + xoff + 8 * PITCH;                        // s-block mt + 1 starts at staged row 8
     uint16_t* out = out_base + (long long)(8 * mt + 3 + rb_row) * C;
     // z-tile m from s-blocks m (prev) and m + 1 (cur, computed here)
     auto step = [&](int i, const SFrag& prev, SFrag& cur) -> bool {
@@ -364,28 +367,64 @@ __global__ void __launch_bounds__(32 * NG) amp_mma_kernel(const __grid_constant_
     }
   };
 
+  // bf16 input: 16-byte cp.async straight into the tile buffer (replicate clamp = clamped source row,
+  // channels past C = zero-fill), tile k+1 in flight while tile k is computed
+  auto async_tile = [&](int tile, int buf) {
+    const int R0 = 8 * (-1 + tile * AM_NB) - 3;
+    const uint32_t dst0 = amm::smem_u32(smem) + (uint32_t)(buf * PLANE);
+#pragma unroll
+    for (int it = 0; it < NV; ++it) {
+      const int idx = tid + it * NT;
+      const int r = idx / VPR, cv = idx - r * VPR;
+      const int t = min(max(R0 + r, 0), L - 1);
+      const int ch = c0 + cv * VEC;
+      const uint16_t* src = reinterpret_cast<const uint16_t*>(p.x) + item + (long long)t * C + (ch < C ? ch : 0);
+      const uint32_t nbytes = ch < C ? 16u : 0u;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (uint32_t)(r * PITCH + cv * 16)), "l"(src), "r"(nbytes) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
   const int tile0 = cti * p.tiles_per_cta;
   const int tile_end = min(tile0 + p.tiles_per_cta, p.n_tiles);
-  load_tile(tile0);
-  store_tile();
+  if constexpr (IN_BF16) {
+    async_tile(tile0, 0);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else {
+    load_tile(tile0);
+    store_tile();
+  }
   __syncthreads();
+  int buf = 0;
   for (int tile = tile0; tile < tile_end; ++tile) {
     const int mt = -1 + tile * AM_NB;  // first z-tile of the staged tile
     const bool has_next = tile + 1 < tile_end;
-    if (has_next) load_tile(tile + 1);
+    const uint32_t xoff = IN_BF16 ? (uint32_t)(buf * PLANE) : 0u;
+    if (has_next) {
+      if constexpr (IN_BF16)
+        async_tile(tile + 1, buf ^ 1);
+      else
+        load_tile(tile + 1);
+    }
     if (tile == tile0) {
       // warm-up: s-block mt (rows from 0), or block 0 (rows from 8) broadcast as block -1
-      s_block(std::true_type{}, mt, ld_base + (mt < 0 ? 8 * PITCH : 0), fa);
+      s_block(std::true_type{}, mt, ld_base + xoff + (mt < 0 ? 8 * PITCH : 0), fa);
     }
     const bool edge = mt < 0 || 16 * (mt + AM_NB) + 15 >= jl;
     if (edge)
-      run_tile(std::true_type{}, mt);
+      run_tile(std::true_type{}, mt, xoff);
     else
-      run_tile(std::false_type{}, mt);
+      run_tile(std::false_type{}, mt, xoff);
     if (!has_next) break;
-    __syncthreads();  // every warp is done with this tile's rows
-    store_tile();
-    __syncthreads();
+    if constexpr (IN_BF16) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();  // the next tile has landed for everyone, and every warp is done with this one
+      buf ^= 1;
+    } else {
+      __syncthreads();  // every warp is done with this tile's rows
+      store_tile();
+      __syncthreads();
+    }
   }
 }
 
@@ -405,7 +444,7 @@ static cudaError_t launch_amp_mma_ng(const AmpMmaParams& p, int ng, cudaStream_t
 
 int amp_mma_tiles = 0;   // test/tuning hook ("amp_mma_tiles"): time tiles per CTA, 0 = choose
 // test/tuning hook (bvg_set_tuning "amp_mma"): 0 = never, 1 = where it measured faster than the FFMA2
-// kernel on B200 (profiles/r01_amp_ab.txt: BF16 -> BF16 with C >= 192), 2 = wherever it is supported
+// kernel on B200 (profiles/r01_ncu_summary_v7.md section 4: BF16 -> BF16 with C >= 48), 2 = wherever it is supported
 int amp_mma_enable = 1;
 
 // The tensor-core kernel takes F32 -> SPLIT (fp32 path) and BF16 -> BF16 (bf16 path) with C a multiple
@@ -416,7 +455,7 @@ bool amp_mma_supported(const bvg_amp_desc* d) {
   const bool f32_split = d->x.dtype == BVG_F32 && d->y.dtype == BVG_SPLIT;
   const bool bf_bf = d->x.dtype == BVG_BF16 && d->y.dtype == BVG_BF16;
   if (!f32_split && !bf_bf) return false;
-  if (amp_mma_enable == 1 && !(bf_bf && d->C >= 192)) return false;
+  if (amp_mma_enable == 1 && !(bf_bf && d->C >= 48)) return false;
   if (((uintptr_t)d->x.d_ptr & 15) || ((uintptr_t)d->y.d_ptr & 15) || (d->y.d_lo && ((uintptr_t)d->y.d_lo & 15))) return false;
   return true;
 }
