@@ -21,6 +21,8 @@
 // ldmatrix.trans builds the channel-major A fragments, stmatrix.trans transposes the result
 // back and every global store is a 16-byte piece of a channels-last row.
 // Index arithmetic is pinned by the lane-level emulation tests/amp_mma_emulation.py.
+#include <cuda_fp16.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -70,6 +72,19 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
+// same shape with fp16 operands
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// (a, b) -> packed fp16 pair, round to nearest, saturating at +-65504 instead of overflowing to inf
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %2, %1;" : "=r"(r) : "f"(a), "f"(b));  // first source -> upper half
+  return r;
+}
 // d += A(16x8, row) * B(8x8, col), tf32 operands (fp32 registers), fp32 accumulate
 __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -130,7 +145,11 @@ __global__ void __launch_bounds__(32 * NG) amp_mma_kernel(const __grid_constant_
   // How the activated signal s enters the down-MMA.  SPLIT output (fp32 path): bf16 hi + lo, three k16
   // MMAs per s-block.  BF16 output: one tf32 term (cvt.rna, 11 significant bits: 4x finer than the bf16
   // the result is rounded to, and no exponent-range concern), k8 MMAs straight from the fp32 registers.
-  constexpr bool S_SPLIT = true;  // tf32 k8 MMAs measured slower on B200 (legacy HMMA pipe is the limit): kept for reference
+  //   S_F16 (BF16 output): s and the low-pass taps as single fp16 terms -- 11 significant bits, 8x finer than the
+  //   bf16 the result is rounded to (a single *bf16* s term costs the bf16 path 0.5 dB and its log-mel gate);
+  //   |s| above 65504 saturates.  2 HMMAs per z-tile instead of 6, no split arithmetic.
+  constexpr bool S_F16 = OUT_MODE == BVG_BF16;
+  constexpr bool S_SPLIT = true;  // (else-branch below: tf32 k8 MMAs, measured slower on B200 -- kept for reference)
   constexpr int PLANE = AM_ROWS * PITCH;
   constexpr int STG_PLANE = 8 * 48;   // 8 rows x 16 channels, 48-byte pitch (conflict-free stmatrix)
   constexpr int STG = STG_PLANE * NOUT;
@@ -164,7 +183,10 @@ __global__ void __launch_bounds__(32 * NG) amp_mma_kernel(const __grid_constant_
     for (int r = 0; r < 2; ++r) {
       const int k = 8 * r + 2 * q;
       amm::split_pair(amm::up_coeff(p, k, 8 * h + rw), amm::up_coeff(p, k + 1, 8 * h + rw), up_hi[h][r], up_lo[h][r]);
-      if constexpr (S_SPLIT) {
+      if constexpr (S_F16) {
+        dn_hi[h][r] = amm::pack_f16x2_sat(amm::down_coeff(p, 16 * h + k, rw), amm::down_coeff(p, 16 * h + k + 1, rw));
+        dn_lo[h][r] = 0u;
+      } else if constexpr (S_SPLIT) {
         amm::split_pair(amm::down_coeff(p, 16 * h + k, rw), amm::down_coeff(p, 16 * h + k + 1, rw), dn_hi[h][r], dn_lo[h][r]);
       } else {
 #pragma unroll
@@ -251,7 +273,12 @@ __global__ void __launch_bounds__(32 * NG) amp_mma_kernel(const __grid_constant_
           }
       }
     }
-    if constexpr (S_SPLIT) {
+    if constexpr (S_F16) {
+      out.hi[0] = amm::pack_f16x2_sat(d[0][0], d[0][1]);
+      out.hi[1] = amm::pack_f16x2_sat(d[0][2], d[0][3]);
+      out.hi[2] = amm::pack_f16x2_sat(d[1][0], d[1][1]);
+      out.hi[3] = amm::pack_f16x2_sat(d[1][2], d[1][3]);
+    } else if constexpr (S_SPLIT) {
       amm::split_pair(d[0][0], d[0][1], out.hi[0], out.lo[0]);
       amm::split_pair(d[0][2], d[0][3], out.hi[1], out.lo[1]);
       amm::split_pair(d[1][0], d[1][1], out.hi[2], out.lo[2]);
@@ -265,7 +292,9 @@ __global__ void __launch_bounds__(32 * NG) amp_mma_kernel(const __grid_constant_
   };
   // z (+)= s-block `f` (blk 0: the older one) through the low-pass Toeplitz fragments
   auto down = [&](float (&z)[4], const SFrag& f, int blk) {
-    if constexpr (S_SPLIT) {
+    if constexpr (S_F16) {
+      amm::mma_f16(z, f.hi, dn_hi[blk]);
+    } else if constexpr (S_SPLIT) {
       amm::mma_bf16(z, f.hi, dn_hi[blk]);
       amm::mma_bf16(z, f.hi, dn_lo[blk]);
       amm::mma_bf16(z, f.lo, dn_hi[blk]);
@@ -444,7 +473,7 @@ static cudaError_t launch_amp_mma_ng(const AmpMmaParams& p, int ng, cudaStream_t
 
 int amp_mma_tiles = 0;   // test/tuning hook ("amp_mma_tiles"): time tiles per CTA, 0 = choose
 // test/tuning hook (bvg_set_tuning "amp_mma"): 0 = never, 1 = where it measured faster than the FFMA2
-// kernel on B200 (profiles/r01_ncu_summary_v7.md section 4: BF16 -> BF16 with C >= 48), 2 = wherever it is supported
+// kernel on B200 (profiles/r01_ncu_summary_v7.md section 4: BF16 -> BF16, every C that is a multiple of 8), 2 = wherever it is supported
 int amp_mma_enable = 1;
 
 // The tensor-core kernel takes F32 -> SPLIT (fp32 path) and BF16 -> BF16 (bf16 path) with C a multiple
@@ -455,7 +484,7 @@ bool amp_mma_supported(const bvg_amp_desc* d) {
   const bool f32_split = d->x.dtype == BVG_F32 && d->y.dtype == BVG_SPLIT;
   const bool bf_bf = d->x.dtype == BVG_BF16 && d->y.dtype == BVG_BF16;
   if (!f32_split && !bf_bf) return false;
-  if (amp_mma_enable == 1 && !(bf_bf && d->C >= 48)) return false;
+  if (amp_mma_enable == 1 && !bf_bf) return false;
   if (((uintptr_t)d->x.d_ptr & 15) || ((uintptr_t)d->y.d_ptr & 15) || (d->y.d_lo && ((uintptr_t)d->y.d_lo & 15))) return false;
   return true;
 }

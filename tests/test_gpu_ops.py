@@ -200,7 +200,7 @@ def test_amp_mma_vs_oracle(ops, shape, mode, fast_sin):
         assert np.abs(y - ref).max() <= scale * 2**-14 + 1e-5, np.abs(y - ref).max()
         assert np.abs(y - y_ffma).max() <= scale * 2**-14 + 1e-5
     else:
-        # s is rounded to bf16 before the low-pass (the FFMA kernel keeps it in fp32) and the result is bf16
+        # s enters the low-pass MMA as fp16 (11 significant bits; the FFMA kernel keeps it in fp32) and the result is bf16
         assert np.abs(y - ref).max() <= scale * 2**-7 + 1e-5, np.abs(y - ref).max()
         np.testing.assert_array_equal(y, bf16_round(y))
         rel = np.sqrt(((y - ref) ** 2).sum() / (ref**2).sum())
