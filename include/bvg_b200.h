@@ -102,7 +102,8 @@ typedef struct bvg_conv_weights {
   int32_t cin_pad;     /* K extent of the packed weights: SIMT round_up(cin,4), UMMA round_up(cin,64) */
   int32_t x_pitch;     /* channel pitch the x tensor must have: SIMT round_up(cin,4), UMMA round_up(cin,8) */
   int32_t tap_stride;  /* tap slots reserved per N tile in the packed planes (>= max n_taps) */
-  int32_t split;       /* UMMA: 1 = hi and lo planes packed (fp32-parity path) */
+  int32_t split;       /* UMMA: 1 = hi and lo planes packed (fp32-parity path); 2 = both planes stacked along N in d_w
+                          (rows [0, n_tile) hi, [n_tile, 2 n_tile) lo per tap; chosen by bvg_conv_geometry for n_tile <= 128) */
   int32_t n_taps[BVG_MAX_NTILES];                  /* taps of each N tile */
   int32_t shift[BVG_MAX_NTILES][BVG_MAX_TAPS];    /* input row shift of each tap */
   void* d_w;           /* SIMT: float [tile][tap][cin_pad][n_tile]; UMMA: bf16 [tile][tap][n_tile][cin_pad] */
@@ -241,7 +242,7 @@ void bvg_program_destroy(bvg_program* p);
 int bvg_abi_version(void);
 const char* bvg_last_error(void);
 int bvg_device_check(int device); /* BVG_OK iff `device` is compute capability 10.x */
-int bvg_set_tuning(const char* name, int value); /* test / tuning knobs: amp_vec, amp_chunk, amp_mma, amp_mma_tiles, amp_packed, umma_mb, umma_wide_mb2, umma_max_ctas, umma_ntile_cap, umma_tap_group */
+int bvg_set_tuning(const char* name, int value); /* test / tuning knobs: amp_vec, amp_chunk, amp_mma, amp_mma_tiles, amp_packed, umma_mb, umma_wide_mb2, umma_max_ctas, umma_ntile_cap, umma_tap_group, umma_a_stages, umma_stack */
 size_t bvg_sizeof_op(void);       /* ABI self-check for the ctypes mirror */
 size_t bvg_sizeof_conv_weights(void);
 

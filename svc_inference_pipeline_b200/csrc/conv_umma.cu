@@ -48,6 +48,7 @@ struct UmmaParams {
   CUtensorMap tm_w[2];  // weight planes (hi, lo)
   EpiParams epi;
   int planes;           // 1 (BF16) or 2 (SPLIT)
+  int stacked;          // SPLIT with both weight planes stacked along N (rows [0,n) hi, [n,2n) lo per tap)
   int B, L, N;
   int n_tile, n_tiles, tap_stride;
   int n_cb;             // Cin slices
@@ -218,10 +219,11 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
 // advance by immediate adds, and the row shift of the next tap is fetched before this tap's MMAs.
 //   sh      : shift of the first tap of the stage (prefetched by the caller, before the barrier wait)
 //   nxt_tap : tap whose shift is to be returned for the caller's next stage
-template <int KS, bool WITH_LO>
+//   STACKED : the stage holds [W_hi; W_lo] per tap: A_hi x both (idesc2, N = 2 n_tile) then A_lo x W_hi (idesc, N = n_tile)
+template <int KS, bool WITH_LO, bool STACKED = false>
 __device__ __forceinline__ int issue_stage(const UmmaParams& p, const int* __restrict__ shifts, int g0, int gtaps, int sh, int nxt_tap,
                                            int min_shift, uint32_t a_stage16, uint32_t b16, uint32_t tmem_acc, uint32_t a_plane16, uint32_t idesc,
-                                           uint64_t desc_hi, uint32_t acc0, uint32_t b_tap16, uint32_t col_stride, int mb) {
+                                           uint64_t desc_hi, uint32_t acc0, uint32_t b_tap16, uint32_t col_stride, int mb, uint32_t idesc2 = 0) {
   for (int g = 0; g < gtaps; ++g) {
     uint32_t a16 = a_stage16 + (uint32_t)(sh - min_shift) * 8u;  // 128 B per row
     sh = shifts[g + 1 < gtaps ? g0 + g + 1 : nxt_tap];
@@ -231,7 +233,7 @@ __device__ __forceinline__ int issue_stage(const UmmaParams& p, const int* __res
 #pragma unroll
       for (int k = 0; k < KS; ++k) {
         const uint64_t bd = desc_hi | (uint64_t)(b16 + 2u * k);
-        if (ptx::elect_one()) ptx::umma_f16(tmem_d, desc_hi | (uint64_t)(a16 + 2u * k), bd, idesc, k == 0 ? first : 1u);
+        if (ptx::elect_one()) ptx::umma_f16(tmem_d, desc_hi | (uint64_t)(a16 + 2u * k), bd, STACKED ? idesc2 : idesc, k == 0 ? first : 1u);
         if (WITH_LO) {
           if (ptx::elect_one()) ptx::umma_f16(tmem_d, desc_hi | (uint64_t)(a16 + a_plane16 + 2u * k), bd, idesc, 1u);
         }
@@ -276,7 +278,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
     ptx::prefetch_tmap(&p.tm_w[0]);
     if (p.planes == 2) {
       ptx::prefetch_tmap(&p.tm_x[1]);
-      ptx::prefetch_tmap(&p.tm_w[1]);
+      if (!p.stacked) ptx::prefetch_tmap(&p.tm_w[1]);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -335,13 +337,15 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
           if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
           // weights: one box of tap_group consecutive taps per (group, plane); rows past the last
           // tap of this N tile belong to the next tile (or are zero-filled past the end) and are unused
+          const int w_planes = p.stacked ? 1 : planes;   // stacked: hi and lo rows arrive in one box
+          const int w_rows = p.stacked ? 2 * p.n_tile : p.n_tile;
           for (int g0 = 0; g0 < ntaps; g0 += p.tap_group) {
-            for (int wp = 0; wp < planes; ++wp) {
+            for (int wp = 0; wp < w_planes; ++wp) {
               ptx::mbar_wait(b_empty(sb), pb ^ 1, p.err_flag, 2);
               if (ptx::elect_one()) {
                 ptx::mbar_expect_tx(b_full(sb), (uint32_t)p.b_stage_bytes);
                 ptx::tma_load_2d(b_base + sb * p.b_stage_bytes, &p.tm_w[wp], b_full(sb), cb * UM_KB,
-                                 (nt * p.tap_stride + g0) * p.n_tile);
+                                 (nt * p.tap_stride + g0) * w_rows);
               }
               __syncwarp();
               if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
@@ -365,7 +369,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
       const bool split = p.planes == 2;
       const int tap_group = p.tap_group;
       const int mb = p.mb;
-      const uint32_t b_tap16 = (uint32_t)p.n_tile * 8u;  // n_tile rows of 128 B per tap
+      const bool stacked = p.stacked != 0;
+      const uint32_t idesc2 = make_idesc(2 * p.n_tile);
+      const uint32_t b_tap16 = (uint32_t)p.n_tile * (stacked ? 16u : 8u);  // rows of 128 B per tap
       const uint32_t col_stride = (uint32_t)p.col_stride;
       const int ks_last = (p.cin - (p.n_cb - 1) * UM_KB + 15) >> 4;
       int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, ap = 0;
@@ -388,8 +394,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
             const uint32_t acc0 = (cb == 0 && g0 == 0) ? 0u : 1u;  // 0 => the first tap overwrites the accumulator
             // one straight-line body per (K steps, lo plane) combination, chosen once per stage
 #define BVG_ISSUE(KS, LO, NXT, ACC)                                                                                                          \
-  sh = issue_stage<KS, LO>(p, shifts, g0, gtaps, sh, NXT, min_shift, a_stage16, b16, tmem_acc, a_plane16, idesc, desc_hi, ACC, b_tap16, \
-                           col_stride, mb)
+  sh = (LO && stacked) ? issue_stage<KS, true, true>(p, shifts, g0, gtaps, sh, NXT, min_shift, a_stage16, b16, tmem_acc, a_plane16, idesc,    \
+                                                      desc_hi, ACC, b_tap16, col_stride, mb, idesc2)                                          \
+                       : issue_stage<KS, LO>(p, shifts, g0, gtaps, sh, NXT, min_shift, a_stage16, b16, tmem_acc, a_plane16, idesc, desc_hi,   \
+                                             ACC, b_tap16, col_stride, mb)
 #define BVG_STAGE(LO, NXT, ACC)                                                              \
   {                                                                                          \
     ptx::mbar_wait(b_full(sb), pb, p.err_flag, 5);                                           \
@@ -403,7 +411,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
     __syncwarp();                                                                            \
     if (++sb == p.b_stages) { sb = 0; pb ^= 1; }                                             \
   }
-            if (split) {
+            if (stacked) {
+              BVG_STAGE(true, g_next, acc0);   // [W hi; W lo] in one stage: A hi x both, A lo x W hi
+            } else if (split) {
               BVG_STAGE(true, g0, acc0);       // W hi: A hi and A lo
               BVG_STAGE(false, g_next, 1u);    // W lo: A hi
             } else {
@@ -495,6 +505,13 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
           if (tbase >= p.L) continue;  // whole 32-row slab past the end of the sequence (warp-uniform)
           uint32_t r[16];
           ptx::tmem_ld16(tmem_q + (uint32_t)(mbi * p.col_stride + c0), r);
+          if (p.stacked) {  // the hi*lo products were accumulated n_tile columns further
+            uint32_t r2[16];
+            ptx::tmem_ld16(tmem_q + (uint32_t)(mbi * p.col_stride + p.n_tile + c0), r2);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+          }
           ptx::tmem_ld_wait();
           // stage: thread = row `lane`; granule gg of row r lives at r*64 + ((gg ^ ((r >> 1) & 3)) * 16)
           const uint32_t wsw = (uint32_t)((lane >> 1) & 3);
@@ -677,7 +694,9 @@ int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out) {
   BVG_REQUIRE(w->backend == BVG_UMMA, "conv_umma: weights were packed for another backend");
   BVG_REQUIRE(d->x.dtype == BVG_BF16 || d->x.dtype == BVG_SPLIT, "conv_umma: input must be BF16 or SPLIT");
   const int planes = d->x.dtype == BVG_SPLIT ? 2 : 1;
-  BVG_REQUIRE(planes == 1 || (w->split && w->d_w_lo && d->x.d_lo), "conv_umma: SPLIT input needs split-packed weights and a lo plane");
+  BVG_REQUIRE(planes == 1 || (w->split && (w->split == 2 || w->d_w_lo) && d->x.d_lo), "conv_umma: SPLIT input needs split-packed weights and a lo plane");
+  const bool stacked = planes == 2 && w->split == 2;
+  BVG_REQUIRE(!stacked || 2 * w->n_tile <= 256, "conv_umma: stacked weights need n_tile <= 128");
   BVG_REQUIRE(d->x.d_ptr && w->d_w, "conv_umma: null pointer");
   BVG_REQUIRE(d->B > 0 && d->L > 0, "conv_umma: bad shape");
   BVG_REQUIRE(w->n_tile % 16 == 0 && w->n_tile >= 16 && w->n_tile <= 256, "conv_umma: bad n_tile %d", w->n_tile);
@@ -690,6 +709,7 @@ int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out) {
   int rc = fill_epilogue(d, p.epi);
   if (rc != BVG_OK) return rc;
   p.planes = planes;
+  p.stacked = stacked ? 1 : 0;
   p.B = d->B;
   p.L = d->L;
   p.N = w->n_total;
@@ -722,13 +742,14 @@ int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out) {
   // latencies (TMA round trip, accumulator hand-over, epilogue) are paid once per mb*128 rows.
   // Constraints: >= 2 accumulator stages in the 512 TMEM columns, >= 3 weight stages in shared
   // memory next to two A super-tiles, and enough tiles to fill the machine twice.
-  p.col_stride = (w->n_tile + 31) / 32 * 32;
+  const int w_rows = stacked ? 2 * w->n_tile : w->n_tile;  // weight rows per tap in a stage = accumulator columns
+  p.col_stride = (w_rows + 31) / 32 * 32;
   int mb = 1;
   for (int cand = UM_MAX_MB; cand >= 1; cand >>= 1) {
     int br, nb, tg;
     const bool tmem_ok = cand * p.col_stride * 2 <= 512 || (cand == 1) || (umma_wide_mb2 && cand == 2 && cand * p.col_stride <= 512);
     if (!tmem_ok) continue;
-    if (plan_smem(cand, 2, max_span, planes, w->n_tile, max_taps, &br, &nb, &tg) < (cand == 1 ? 2 : 3)) continue;
+    if (plan_smem(cand, 2, max_span, planes, w_rows, max_taps, &br, &nb, &tg) < (cand == 1 ? 2 : 3)) continue;
     const long long tiles = (long long)d->B * ceil_div(d->L, cand * UM_BM) * w->n_tiles;
     if (cand > 1 && tiles < 2ll * sms) continue;
     mb = cand;
@@ -748,19 +769,19 @@ int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out) {
   int a_stages = 2;
   for (int cand = UM_MAX_A_STAGES; cand > 2; --cand) {
     int br, nb, tg;
-    if (umma_a_stages == -1 && p.n_cb <= 2 && plan_smem(mb, cand, max_span, planes, w->n_tile, max_taps, &br, &nb, &tg) >= 3) {
+    if (umma_a_stages == -1 && p.n_cb <= 2 && plan_smem(mb, cand, max_span, planes, w_rows, max_taps, &br, &nb, &tg) >= 3) {
       a_stages = cand;
       break;
     }
   }
   if (umma_a_stages >= 2 && umma_a_stages <= UM_MAX_A_STAGES) a_stages = umma_a_stages;
   p.a_stages = a_stages;
-  const int bs = plan_smem(mb, a_stages, max_span, planes, w->n_tile, max_taps, &p.a_box_rows, &p.a_boxes, &p.tap_group);
+  const int bs = plan_smem(mb, a_stages, max_span, planes, w_rows, max_taps, &p.a_box_rows, &p.a_boxes, &p.tap_group);
   BVG_REQUIRE(bs >= 2, "conv_umma: tile does not fit in shared memory (mb %d, span %d, n_tile %d, planes %d)", mb, max_span, w->n_tile, planes);
   p.b_stages = bs;
   p.a_plane_bytes = p.a_boxes * p.a_box_rows * 128;
   p.a_stage_bytes = p.a_plane_bytes * planes;
-  p.b_stage_bytes = p.tap_group * w->n_tile * 128;
+  p.b_stage_bytes = p.tap_group * w_rows * 128;
   size_t smem = 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)bs * p.b_stage_bytes + UM_STAGING_BYTES + kBarBytes;
   // keep one CTA per SM (each allocates all 512 TMEM columns): ask for more than half the SM's smem
   if (smem < 120 * 1024) smem = 120 * 1024;
@@ -776,9 +797,10 @@ int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out) {
     rc = encode_bf16_map(&p.tm_x[pl], xb, 3, dims, strides, box, "activation");
     if (rc != BVG_OK) return rc;
     void* wb = pl == 0 ? w->d_w : w->d_w_lo;
-    cuuint64_t wdims[2] = {(cuuint64_t)w->cin_pad, (cuuint64_t)w->n_tiles * w->tap_stride * w->n_tile};
+    if (stacked && pl == 1) continue;  // both weight planes live in d_w
+    cuuint64_t wdims[2] = {(cuuint64_t)w->cin_pad, (cuuint64_t)w->n_tiles * w->tap_stride * w_rows};
     cuuint64_t wstrides[1] = {(cuuint64_t)w->cin_pad * 2};
-    cuuint32_t wbox[2] = {(cuuint32_t)UM_KB, (cuuint32_t)(p.tap_group * w->n_tile)};
+    cuuint32_t wbox[2] = {(cuuint32_t)UM_KB, (cuuint32_t)(p.tap_group * w_rows)};
     rc = encode_bf16_map(&p.tm_w[pl], wb, 2, wdims, wstrides, wbox, "weights");
     if (rc != BVG_OK) return rc;
   }

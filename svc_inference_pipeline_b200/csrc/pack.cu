@@ -35,7 +35,7 @@ struct PackParams {
   const float* v;
   const float* scale;
   int transposed, cin, cout, ksize, dilation, stride, padding;
-  int backend, n_total, n_tile, n_tiles, cin_pad, tap_stride;
+  int backend, n_total, n_tile, n_tiles, cin_pad, tap_stride, stacked;
   int n_taps[BVG_MAX_NTILES];
   int shift[BVG_MAX_NTILES][BVG_MAX_TAPS];
   float* out_f32;
@@ -66,7 +66,7 @@ __device__ __forceinline__ float folded_weight(const PackParams& p, int n, int c
 __global__ void pack_weights_kernel(const __grid_constant__ PackParams p) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= p.total) return;
-  int tile, slot, nl, ci;
+  int tile, slot, nl, ci, plane = 0;
   if (p.backend == BVG_SIMT) {  // [tile][slot][ci][nl]
     nl = (int)(idx % p.n_tile);
     long long r = idx / p.n_tile;
@@ -74,11 +74,15 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackParams p) {
     r /= p.cin_pad;
     slot = (int)(r % p.tap_stride);
     tile = (int)(r / p.tap_stride);
-  } else {  // [tile][slot][nl][ci]
+  } else {  // [tile][slot][nl][ci]   (stacked: [tile][slot][plane][nl][ci])
     ci = (int)(idx % p.cin_pad);
     long long r = idx / p.cin_pad;
     nl = (int)(r % p.n_tile);
     r /= p.n_tile;
+    if (p.stacked) {
+      plane = (int)(r & 1);
+      r >>= 1;
+    }
     slot = (int)(r % p.tap_stride);
     tile = (int)(r / p.tap_stride);
   }
@@ -90,8 +94,12 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackParams p) {
   } else {
     float hi, lo;
     split_bf16(w, hi, lo);
-    p.out_hi[idx] = (uint16_t)float_to_bf16_bits(hi);
-    if (p.out_lo) p.out_lo[idx] = (uint16_t)float_to_bf16_bits(lo);
+    if (p.stacked) {
+      p.out_hi[idx] = (uint16_t)float_to_bf16_bits(plane ? lo : hi);
+    } else {
+      p.out_hi[idx] = (uint16_t)float_to_bf16_bits(hi);
+      if (p.out_lo) p.out_lo[idx] = (uint16_t)float_to_bf16_bits(lo);
+    }
   }
 }
 
@@ -102,6 +110,7 @@ __global__ void pack_bias_kernel(const float* __restrict__ bias, int cout, int n
 }
 
 int umma_ntile_cap = 256;  // tuning hook: widest UMMA N tile chosen by conv_geometry (multiple of 16)
+int umma_stack = 128;      // tuning hook: widest n_tile whose (hi, lo) weight planes are stacked along N (0 = never)
 
 static int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -142,6 +151,10 @@ int conv_geometry(const bvg_conv_geom* g, bvg_conv_weights* w) {
   }
   w->n_tile = n_tile;
   w->n_tiles = ceil_div(n_total, n_tile);
+  // Narrow split layers: both weight planes in ONE operand, rows [0, n_tile) = hi, [n_tile, 2 n_tile) = lo
+  // per tap ("stacked", split = 2).  A_hi x [W_hi; W_lo] is then a single MMA of width 2 n_tile, so a product
+  // costs two reads of the A tile from shared memory instead of three (these layers are bound by exactly that).
+  if (w->split && n_tile <= umma_stack && n_tile <= 128) w->split = 2;
   const int n_tables = (g->backend == BVG_SIMT) ? 1 : w->n_tiles;
   BVG_REQUIRE(n_tables <= BVG_MAX_NTILES, "conv geometry: %d N tiles exceed BVG_MAX_NTILES", w->n_tiles);
   for (int t = 0; t < BVG_MAX_NTILES; ++t) {
@@ -175,7 +188,7 @@ int conv_geometry(const bvg_conv_geom* g, bvg_conv_weights* w) {
 }
 
 size_t conv_plane_elems(const bvg_conv_weights* w) {
-  return (size_t)w->n_tiles * w->tap_stride * w->n_tile * w->cin_pad;
+  return (size_t)w->n_tiles * w->tap_stride * w->n_tile * w->cin_pad * (w->split == 2 ? 2 : 1);
 }
 
 int pack_conv_weights(const bvg_conv_geom* g, const float* d_v, const float* d_g, const float* d_bias, bvg_conv_weights* w,
@@ -183,7 +196,7 @@ int pack_conv_weights(const bvg_conv_geom* g, const float* d_v, const float* d_g
   int rc = conv_geometry(g, w);
   if (rc != BVG_OK) return rc;
   BVG_REQUIRE(d_v && w->d_w && d_bias_out && d_scale_scratch, "pack weights: null pointer");
-  BVG_REQUIRE(!w->split || w->d_w_lo, "pack weights: split packing needs d_w_lo");
+  BVG_REQUIRE(w->split != 1 || w->d_w_lo, "pack weights: split packing needs d_w_lo");
   const int dim0 = g->transposed ? g->cin : g->cout;
   const int inner = (g->transposed ? g->cout : g->cin) * g->ksize;
   wn_scale_kernel<<<dim0, 256, 0, st>>>(d_v, d_g, inner, d_scale_scratch);
@@ -205,13 +218,14 @@ int pack_conv_weights(const bvg_conv_geom* g, const float* d_v, const float* d_g
   p.n_tiles = w->n_tiles;
   p.cin_pad = w->cin_pad;
   p.tap_stride = w->tap_stride;
+  p.stacked = w->split == 2;
   for (int t = 0; t < BVG_MAX_NTILES; ++t) {
     p.n_taps[t] = w->n_taps[t];
     for (int k = 0; k < BVG_MAX_TAPS; ++k) p.shift[t][k] = w->shift[t][k];
   }
   p.out_f32 = (w->backend == BVG_SIMT) ? reinterpret_cast<float*>(w->d_w) : nullptr;
   p.out_hi = (w->backend == BVG_UMMA) ? reinterpret_cast<uint16_t*>(w->d_w) : nullptr;
-  p.out_lo = (w->backend == BVG_UMMA && w->split) ? reinterpret_cast<uint16_t*>(w->d_w_lo) : nullptr;
+  p.out_lo = (w->backend == BVG_UMMA && w->split == 1) ? reinterpret_cast<uint16_t*>(w->d_w_lo) : nullptr;
   p.total = (long long)conv_plane_elems(w);
   const long long blocks = ceil_div_ll(p.total, 256);
   BVG_REQUIRE(blocks < (1ll << 31), "pack weights: too large");

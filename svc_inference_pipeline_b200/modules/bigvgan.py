@@ -168,11 +168,13 @@ class _PackedConv:
         )
         wb, bb = C.c_size_t(), C.c_size_t()
         L.check(lib.bvg_conv_pack_bytes(C.byref(self.geom), C.byref(wb), C.byref(bb)), "conv_pack_bytes")
+        self.desc = L.ConvWeights()
+        L.check(lib.bvg_conv_geometry(C.byref(self.geom), C.byref(self.desc)), "conv_geometry")
         self.w_hi = torch.empty(wb.value, dtype=torch.uint8, device=dev)
-        self.w_lo = torch.empty(wb.value, dtype=torch.uint8, device=dev) if (split and backend == L.UMMA) else None
+        # split == 2: narrow layer, both planes stacked along N inside w_hi (no separate lo plane)
+        self.w_lo = torch.empty(wb.value, dtype=torch.uint8, device=dev) if (self.desc.split == 1 and backend == L.UMMA) else None
         self.bias = torch.empty(bb.value // 4, dtype=torch.float32, device=dev)
         scratch = torch.empty(max(conv.cin, conv.cout), dtype=torch.float32, device=dev)
-        self.desc = L.ConvWeights()
         self.desc.d_w = self.w_hi.data_ptr()
         self.desc.d_w_lo = self.w_lo.data_ptr() if self.w_lo is not None else None
         v = conv.weight_v.detach().contiguous().float()
