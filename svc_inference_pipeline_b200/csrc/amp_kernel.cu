@@ -441,6 +441,8 @@ static cudaError_t launch_amp_vec(const AmpParams& p, bool in_bf16, int out_mode
 
 bool amp_mma_supported(const bvg_amp_desc* d);               // amp_mma.cu: tensor-core FIR variant
 int amp_mma_forward(const bvg_amp_desc* d, cudaStream_t st);
+bool amp_stream_supported(const bvg_amp_desc* d);            // amp_stream.cu: per-warp streaming variant (F32 -> SPLIT)
+int amp_stream_forward(const bvg_amp_desc* d, cudaStream_t st);
 
 int amp_vec_override = 0;  // test/tuning hook: force VEC (set through bvg_set_tuning)
 int amp_chunk_override = 0;
@@ -457,6 +459,7 @@ int amp_forward(const bvg_amp_desc* d, cudaStream_t st) {
   // the two operand formats of the generator (F32 -> SPLIT, BF16 -> BF16) run the FIRs on the
   // tensor cores; every other combination stays on the FFMA kernel below
   if (amp_mma_supported(d)) return amp_mma_forward(d, st);
+  if (amp_stream_supported(d)) return amp_stream_forward(d, st);
 
   // two channels per thread: measured 15-25 % faster than four on B200 (64 vs 164 registers ->
   // 2.7x the resident warps; profiles/r01_amp_sweep.txt)
