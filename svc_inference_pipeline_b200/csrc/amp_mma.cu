@@ -135,9 +135,10 @@ __global__ void __launch_bounds__(32 * NG) amp_mma_kernel(const __grid_constant_
       if constexpr (NPL == 2) amm::mma_bf16(d[h], xl, up_hi[h]);
     }
 #pragma unroll
-    for (int h = 0; h < 2; ++h)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) d[h][i] = amm::snake<FAST_SIN>(d[h][i], apar[i >> 1], invb[i >> 1]);
+    for (int h = 0; h < 2; ++h) {  // registers (0, 1) and (2, 3) are two time steps of one channel each
+      amm::snake_pair<FAST_SIN>(d[h][0], d[h][1], apar[0], invb[0]);
+      amm::snake_pair<FAST_SIN>(d[h][2], d[h][3], apar[1], invb[1]);
+    }
     if constexpr (EDGE) {
       if (m < 0) {
         // left clamp (LowPassFilter1d pad, bigvgan.py:227): s[j < 0] = s[0]; `addr` pointed at block 0

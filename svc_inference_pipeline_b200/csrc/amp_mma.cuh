@@ -110,6 +110,29 @@ __device__ __forceinline__ float snake(float u, float apar, float invb) {
   return fmaf(invb, s * s, u);
 }
 
+// snake on two values of the same channel (an accumulator register pair) with Blackwell's two-lane fp32
+// instructions: mul / mul / fma are one instruction each for the pair (the FMA pipe has room in these kernels,
+// the issue slots do not); same operation order as snake<> above, so the results are identical.
+template <bool FAST_SIN>
+__device__ __forceinline__ void snake_pair(float& u0, float& u1, float apar, float invb) {
+  unsigned long long u, a, b, arg, ss, out;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(u) : "f"(u0), "f"(u1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(a) : "f"(apar));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(b) : "f"(invb));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(arg) : "l"(u), "l"(a));
+  float t0, t1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(t0), "=f"(t1) : "l"(arg));
+  if constexpr (!FAST_SIN) {
+    t0 = (t0 - ((t0 + 12582912.0f) - 12582912.0f)) * 3.14159265358979f;
+    t1 = (t1 - ((t1 + 12582912.0f) - 12582912.0f)) * 3.14159265358979f;
+  }
+  const float s0 = __sinf(t0), s1 = __sinf(t1);
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ss) : "f"(s0), "f"(s1));
+  asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(ss) : "l"(ss));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(out) : "l"(b), "l"(ss), "l"(u));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(u0), "=f"(u1) : "l"(out));
+}
+
 }  // namespace amm
 
 }  // namespace bvg
