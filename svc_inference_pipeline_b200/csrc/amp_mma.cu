@@ -209,7 +209,6 @@ __global__ void __launch_bounds__(32 * NG) amp_mma_kernel(const __grid_constant_
   auto run_tile = [&](auto edge_tag, int mt, uint32_t xoff) {
     constexpr bool EDGE = decltype(edge_tag)::value;
     uint32_t addr = ld_base + xoff + 8 * PITCH;                        // s-block mt + 1 starts at staged row 8
-    uint16_t* out = out_base + (long long)(8 * mt + 3 + rb_row) * C;
     // z-tile m from s-blocks m (prev) and m + 1 (cur, computed here)
     auto step = [&](int i, const SFrag& prev, SFrag& cur) -> bool {
       const int m = mt + i;
@@ -236,9 +235,9 @@ __global__ void __launch_bounds__(32 * NG) amp_mma_kernel(const __grid_constant_
         const int t = 8 * m + 3 + rb_row;
         on = on && t >= 0 && t < L;
       }
-      if (on) *reinterpret_cast<uint4*>(out) = *reinterpret_cast<const uint4*>(rb_ptr + sbuf);
+      // (address formed from the row index each time: a pointer carried across the nested lambdas ends up on the stack)
+      if (on) *reinterpret_cast<uint4*>(out_base + (long long)(8 * m + 3 + rb_row) * C) = *reinterpret_cast<const uint4*>(rb_ptr + sbuf);
       addr += 8 * PITCH;
-      out += 8 * (long long)C;
       return true;
     };
     static_assert(AM_NB % 2 == 0, "ping-pong needs an even number of z-tiles per staged tile");
