@@ -458,8 +458,8 @@ int amp_forward(const bvg_amp_desc* d, cudaStream_t st) {
 
   // the two operand formats of the generator (F32 -> SPLIT, BF16 -> BF16) run the FIRs on the
   // tensor cores; every other combination stays on the FFMA kernel below
-  if (amp_mma_supported(d)) return amp_mma_forward(d, st);
   if (amp_stream_supported(d)) return amp_stream_forward(d, st);
+  if (amp_mma_supported(d)) return amp_mma_forward(d, st);
 
   // two channels per thread: measured 15-25 % faster than four on B200 (64 vs 164 registers ->
   // 2.7x the resident warps; profiles/r01_amp_sweep.txt)

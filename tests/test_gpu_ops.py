@@ -170,7 +170,7 @@ AMP_MMA_SHAPES = [(2, 24, 1000), (1, 768, 301), (3, 8, 97), (2, 40, 64), (1, 48,
 
 
 @pytest.mark.parametrize("shape", AMP_MMA_SHAPES + [(1, 16, ln) for ln in (1, 2, 3, 5, 7, 8, 9, 11, 12, 13, 15, 16, 17, 19, 20, 21, 27, 28)])
-@pytest.mark.parametrize("mode", ["f32_split", "bf16_bf16", "f32_split_stream"])
+@pytest.mark.parametrize("mode", ["f32_split", "bf16_bf16", "f32_split_stream", "bf16_bf16_stream"])
 @pytest.mark.parametrize("fast_sin", [False, True])
 def test_amp_mma_vs_oracle(ops, shape, mode, fast_sin):
     """Tensor-core Activation1d (amp_mma.cu: both FIRs as banded-Toeplitz MMAs) on the two operand
@@ -185,7 +185,7 @@ def test_amp_mma_vs_oracle(ops, shape, mode, fast_sin):
     beta = (rng.standard_normal(Ch) * 0.3).astype(np.float32)
     f = golden_taps()
     a, invb = snake_params(alpha, beta, True)
-    stream = mode == "f32_split_stream"  # amp_stream.cu: the per-warp cp.async ring variant of F32 -> SPLIT
+    stream = mode.endswith("_stream")  # amp_stream.cu: the per-warp cp.async ring variant of either format
     in_dt, out_dt = (L.F32, L.SPLIT) if mode.startswith("f32_split") else (L.BF16, L.BF16)
     x_seen = bf16_round(x) if in_dt == L.BF16 else x
     ref = O.activation1d(x_seen.astype(np.float64), alpha.astype(np.float64), beta.astype(np.float64), True, f.astype(np.float64), f.astype(np.float64))
@@ -193,13 +193,16 @@ def test_amp_mma_vs_oracle(ops, shape, mode, fast_sin):
     try:
         L.set_tuning("amp_mma", 0 if stream else 2)  # force the tensor-core kernel under test for every supported shape
         L.set_tuning("amp_stream", 1 if stream else 0)
+        L.set_tuning("amp_stream_bf16", 1 if stream else 0)
         y = cf(_ops.activation1d(cl(x), a, invb, f, f, in_dtype=in_dt, out_dtype=out_dt, fast_sin=fast_sin))
         L.set_tuning("amp_mma", 0)
         L.set_tuning("amp_stream", 0)
+        L.set_tuning("amp_stream_bf16", 0)
         y_ffma = cf(_ops.activation1d(cl(x), a, invb, f, f, in_dtype=in_dt, out_dtype=out_dt, fast_sin=fast_sin))
     finally:
         L.set_tuning("amp_mma", 1)
         L.set_tuning("amp_stream", 0)
+        L.set_tuning("amp_stream_bf16", 0)
     assert np.isfinite(y).all()
     if out_dt == L.SPLIT:
         # operands carry 16 mantissa bits (hi + lo), products accumulate in fp32
@@ -413,8 +416,8 @@ def test_amp_guard_bands(ops, kernel, mode):
     _ops, L = ops
     if kernel == "mma" and mode == "f32_f32":
         pytest.skip("the tensor-core kernel does not take F32 -> F32")
-    if kernel == "stream" and mode != "f32_split":
-        pytest.skip("the streaming kernel is F32 -> SPLIT only")
+    if kernel == "stream" and mode == "f32_f32":
+        pytest.skip("the streaming kernel does not take F32 -> F32")
     in_dt, out_dt = {"f32_split": (L.F32, L.SPLIT), "bf16_bf16": (L.BF16, L.BF16), "f32_f32": (L.F32, L.F32)}[mode]
     G = 4096
     f = golden_taps()
@@ -438,12 +441,14 @@ def test_amp_guard_bands(ops, kernel, mode):
         try:
             L.set_tuning("amp_mma", 2 if kernel == "mma" else 0)
             L.set_tuning("amp_stream", 1 if kernel == "stream" else 0)
+            L.set_tuning("amp_stream_bf16", 1 if kernel == "stream" else 0)
             L.set_tuning("amp_packed", 0 if kernel == "scalar" else 1)
             L.check(L.lib().bvg_amp_fwd(C.byref(d), torch.cuda.current_stream().cuda_stream), "amp_fwd")
             torch.cuda.synchronize()
         finally:
             L.set_tuning("amp_mma", 1)
             L.set_tuning("amp_stream", 0)
+            L.set_tuning("amp_stream_bf16", 0)
             L.set_tuning("amp_packed", 1)
         for pl in planes:
             assert bool((pl[:G] == sent).all()) and bool((pl[-G:] == sent).all()), (kernel, mode, B, Ch, Ln)
