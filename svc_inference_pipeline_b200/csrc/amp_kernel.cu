@@ -265,11 +265,13 @@ __device__ __forceinline__ P2 add2(P2 a, P2 b) {
 
 template <bool IN_BF16>
 __device__ __forceinline__ P2 load_row2(const void* base, long long off) {
+  // plain (coherent) loads, not ld.global.nc: a load that may alias the output rows stays behind the stores
+  // before it, which bounds how far ptxas sinks the stores of a block (and the registers they hold)
   if constexpr (!IN_BF16) {
-    const float2 t = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(base) + off));
+    const float2 t = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(base) + off);
     return pk2(t.x, t.y);
   } else {
-    const uint32_t t = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(base) + off));
+    const uint32_t t = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(base) + off);
     return pk2(__uint_as_float(t << 16), __uint_as_float(t & 0xffff0000u));
   }
 }
@@ -290,15 +292,27 @@ __device__ __forceinline__ P2 snake_two(P2 u, P2 apar, P2 invb) {
   return fma2(invb, mul2(s, s), u);
 }
 
-template <bool IN_BF16, int OUT_MODE, bool FAST_SIN, bool STORE>
+// INTERIOR: the block touches no sequence end (rows tau0+6 .. tau0+11 exist, tau0+5 < L-3): no clamps, no
+// selects, no store predicate.  CT: compile-time channel count (0 = runtime p.C): with it every row of the
+// block is an immediate offset from one pointer.  Together they remove ~33 of the 85 instructions per step
+// that ncu counted as address arithmetic and edge selects (profiles/r01_ncu_summary_v7.md -> _v13.md).
+template <bool IN_BF16, int OUT_MODE, bool FAST_SIN, bool STORE, bool INTERIOR, int CT>
 __device__ __forceinline__ void amp_block6_p2(const AmpParams& p, const P2 (&xa)[6], P2 (&xb)[6], const P2 (&sa)[12], P2 (&sb)[12], int tau0,
                                               long long base, P2 apar, P2 invb) {
   const int L = p.L;
+  const int Cc = CT ? CT : p.C;
+  if constexpr (INTERIOR) {
+    const long long row0 = base + (long long)(tau0 + 6) * Cc;
 #pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    const int r = min(max(tau0 + 6 + j, 0), L - 1);
-    xb[j] = load_row2<IN_BF16>(p.x, base + (long long)r * p.C);
+    for (int j = 0; j < 6; ++j) xb[j] = load_row2<IN_BF16>(p.x, row0 + j * Cc);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const int r = min(max(tau0 + 6 + j, 0), L - 1);
+      xb[j] = load_row2<IN_BF16>(p.x, base + (long long)r * Cc);
+    }
   }
+  const long long out0 = base + (long long)tau0 * Cc;
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
     P2 pa = 0ull, pb = 0ull;  // +0.0f in both lanes
@@ -312,10 +326,12 @@ __device__ __forceinline__ void amp_block6_p2(const AmpParams& p, const P2 (&xa)
     pa = snake_two<FAST_SIN>(pa, apar, invb);
     pb = snake_two<FAST_SIN>(pb, apar, invb);
     const int tau = tau0 + j;
-    if (tau >= L - 3) {  // right replicate clamp of the activated signal: s[j > 2L-1] = s[2L-1]
-      const P2 prev = (j == 0) ? sa[11] : sb[j == 0 ? 0 : 2 * j - 1];
-      if (tau >= L - 2) pa = prev;
-      pb = pa;
+    if constexpr (!INTERIOR) {
+      if (tau >= L - 3) {  // right replicate clamp of the activated signal: s[j > 2L-1] = s[2L-1]
+        const P2 prev = (j == 0) ? sa[11] : sb[j == 0 ? 0 : 2 * j - 1];
+        if (tau >= L - 2) pa = prev;
+        pb = pa;
+      }
     }
     sb[2 * j] = pa;
     sb[2 * j + 1] = pb;
@@ -327,29 +343,43 @@ __device__ __forceinline__ void amp_block6_p2(const AmpParams& p, const P2 (&xa)
         const P2 sv = (i < 12) ? sa[i < 12 ? i : 0] : sb[i >= 12 ? i - 12 : 0];
         z = fma2(pk2(p.fd[k], p.fd[k]), sv, z);
       }
-      if (tau < L) {
+      if (INTERIOR || tau < L) {
         float zz[2];
         upk2(z, zz[0], zz[1]);
-        store_row<OUT_MODE, 2>(p.y, p.y_lo, base + (long long)tau * p.C, zz);
+        if constexpr (OUT_MODE == BVG_SPLIT) {
+          // hi = bf16(z) for both channels in one F2FP, widened back with a shift and a mask, lo = z - hi in
+          // one packed operation: the values of split_bf16 in 5 instructions instead of 8
+          const uint32_t hi = pack_bf16x2(zz[0], zz[1]);
+          const P2 lo = fma2(pk2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u)), pk2(-1.0f, -1.0f), z);
+          float l0, l1;
+          upk2(lo, l0, l1);
+          *reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(p.y) + out0 + j * Cc) = hi;
+          *reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(p.y_lo) + out0 + j * Cc) = pack_bf16x2(l0, l1);
+        } else {
+          store_row<OUT_MODE, 2>(p.y, p.y_lo, out0 + j * Cc, zz);
+        }
       }
     }
   }
 }
 
-// plain __launch_bounds__(128): ptxas settles at 56-66 registers; forcing 8 resident CTAs (64 registers)
-// spills in the bf16 variants (2.4x slower), allowing 4-6 CTAs' worth of registers is 3-5 % slower (B200)
-template <bool IN_BF16, int OUT_MODE, bool FAST_SIN>
-__global__ void __launch_bounds__(128) amp_kernel_p2(const __grid_constant__ AmpParams p) {
+// __launch_bounds__(128, 6) = 80 registers: the clamp-free loop wants ~96 (5 resident CTAs) and takes a few
+// spills at 80; measured on B200 in-program (gpurun_out/ab_p2ct.txt) 80 beats 96 by 5-10 % for C >= 96 and
+// ties below, 72 and 64 spill heavily.  The bf16 variants spill at 64 (2.4x slower).
+template <bool IN_BF16, int OUT_MODE, bool FAST_SIN, int CT>
+__global__ void __launch_bounds__(128, 6) amp_kernel_p2(const __grid_constant__ AmpParams p) {
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= p.total_threads) return;
-  const int cg = (int)(tid % p.CG);
-  const long long rest = tid / p.CG;
+  const int Cc = CT ? CT : p.C;
+  const int CG = CT ? CT / 2 : p.CG;
+  const int cg = (int)(tid % CG);
+  const long long rest = tid / CG;
   const int chunk = (int)(rest % p.nchunks);
   const int b = (int)(rest / p.nchunks);
   const int TT = 12 * p.nblk2;
   const int t0 = chunk * TT;
   const int L = p.L;
-  const long long base = (long long)b * L * p.C + (long long)cg * 2;
+  const long long base = (long long)b * L * Cc + (long long)cg * 2;
 
   const float a0 = __ldg(p.a + cg * 2), a1 = __ldg(p.a + cg * 2 + 1);
   const P2 apar = FAST_SIN ? pk2(a0, a1) : pk2(a0 * 0.318309886183790672f, a1 * 0.318309886183790672f);
@@ -361,46 +391,82 @@ __global__ void __launch_bounds__(128) amp_kernel_p2(const __grid_constant__ Amp
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
     const int r = min(max(t0 - 6 + k, 0), L - 1);
-    xa[k] = load_row2<IN_BF16>(p.x, base + (long long)r * p.C);
+    xa[k] = load_row2<IN_BF16>(p.x, base + (long long)r * Cc);
   }
-  // warm-up block (tau = t0-6 .. t0-1): fills sb = s[2 t0 - 7 .. 2 t0 + 4], no output
-  amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, false>(p, xa, xb, sa, sb, t0 - 6, base, apar, invb);
-  if (t0 == 0) {  // left replicate clamp of the activated signal: s[j < 0] = s[0] (slot 7)
+  // A chunk whose last block stays clear of the sequence end (rows up to t0 + TT + 5 exist) runs the
+  // clamp-free blocks only; the last chunk of a batch item takes the general path.  Two separate loops:
+  // a per-block choice inside one loop costs registers.
+  if (t0 + TT + 5 <= L - 1) {
+    // warm-up block (tau = t0-6 .. t0-1): fills sb = s[2 t0 - 7 .. 2 t0 + 4], no output
+    amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, false, true, CT>(p, xa, xb, sa, sb, t0 - 6, base, apar, invb);
+    if (t0 == 0) {  // left replicate clamp of the activated signal: s[j < 0] = s[0] (slot 7)
+#pragma unroll
+      for (int k = 0; k < 7; ++k) sb[k] = sb[7];
+    }
+    int t = t0;
+    for (int i = 0; i < p.nblk2; ++i) {
+      amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, true, true, CT>(p, xb, xa, sb, sa, t, base, apar, invb);
+      amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, true, true, CT>(p, xa, xb, sa, sb, t + 6, base, apar, invb);
+      t += 12;
+    }
+    return;
+  }
+  amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, false, false, CT>(p, xa, xb, sa, sb, t0 - 6, base, apar, invb);
+  if (t0 == 0) {
 #pragma unroll
     for (int k = 0; k < 7; ++k) sb[k] = sb[7];
   }
   int t = t0;
   for (int i = 0; i < p.nblk2; ++i) {
     if (t >= L) break;
-    amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, true>(p, xb, xa, sb, sa, t, base, apar, invb);
+    amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, true, false, CT>(p, xb, xa, sb, sa, t, base, apar, invb);
     t += 6;
     if (t >= L) break;
-    amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, true>(p, xa, xb, sa, sb, t, base, apar, invb);
+    amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, true, false, CT>(p, xa, xb, sa, sb, t, base, apar, invb);
     t += 6;
   }
 }
 
 int amp_packed_enable = 1;  // test/tuning hook ("amp_packed"): 0 = scalar FFMA kernel for two channels per thread too
 
-template <bool IN_BF16, int OUT_MODE>
-static cudaError_t launch_amp_p2(const AmpParams& p, bool fast, cudaStream_t st) {
+template <bool IN_BF16, int OUT_MODE, bool FAST_SIN, int CT>
+static cudaError_t launch_amp_p2_ct(const AmpParams& p, cudaStream_t st) {
   const int threads = 128;
   const long long blocks = ceil_div_ll(p.total_threads, threads);
   // Same shared-memory carve-out as the convolution kernel (max shared): an SM can only host kernels of
   // two streams at once when they agree on the L1 / shared split, and this kernel streams through L2 anyway.
-  static bool configured[2] = {false, false};
-  if (!configured[fast ? 1 : 0]) {
-    if (fast)
-      cudaFuncSetAttribute(amp_kernel_p2<IN_BF16, OUT_MODE, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    else
-      cudaFuncSetAttribute(amp_kernel_p2<IN_BF16, OUT_MODE, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    configured[fast ? 1 : 0] = true;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(amp_kernel_p2<IN_BF16, OUT_MODE, FAST_SIN, CT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    configured = true;
   }
-  if (fast)
-    amp_kernel_p2<IN_BF16, OUT_MODE, true><<<(unsigned)blocks, threads, 0, st>>>(p);
-  else
-    amp_kernel_p2<IN_BF16, OUT_MODE, false><<<(unsigned)blocks, threads, 0, st>>>(p);
+  amp_kernel_p2<IN_BF16, OUT_MODE, FAST_SIN, CT><<<(unsigned)blocks, threads, 0, st>>>(p);
   return cudaGetLastError();
+}
+
+int amp_ct_enable = 1;  // tuning hook ("amp_ct"): 0 = runtime channel count for every shape
+
+// the generator's own operand format (F32 -> SPLIT) gets one instantiation per channel count of the
+// repo / v2 generators; everything else runs with the channel count as a kernel parameter
+template <bool IN_BF16, int OUT_MODE, bool FAST_SIN>
+static cudaError_t launch_amp_p2_sin(const AmpParams& p, cudaStream_t st) {
+  if constexpr (!IN_BF16 && OUT_MODE == BVG_SPLIT) {
+    if (amp_ct_enable) switch (p.C) {
+      case 24: return launch_amp_p2_ct<IN_BF16, OUT_MODE, FAST_SIN, 24>(p, st);
+      case 48: return launch_amp_p2_ct<IN_BF16, OUT_MODE, FAST_SIN, 48>(p, st);
+      case 96: return launch_amp_p2_ct<IN_BF16, OUT_MODE, FAST_SIN, 96>(p, st);
+      case 192: return launch_amp_p2_ct<IN_BF16, OUT_MODE, FAST_SIN, 192>(p, st);
+      case 384: return launch_amp_p2_ct<IN_BF16, OUT_MODE, FAST_SIN, 384>(p, st);
+      case 768: return launch_amp_p2_ct<IN_BF16, OUT_MODE, FAST_SIN, 768>(p, st);
+      default: break;
+    }
+  }
+  return launch_amp_p2_ct<IN_BF16, OUT_MODE, FAST_SIN, 0>(p, st);
+}
+
+template <bool IN_BF16, int OUT_MODE>
+static cudaError_t launch_amp_p2(const AmpParams& p, bool fast, cudaStream_t st) {
+  return fast ? launch_amp_p2_sin<IN_BF16, OUT_MODE, true>(p, st) : launch_amp_p2_sin<IN_BF16, OUT_MODE, false>(p, st);
 }
 
 static cudaError_t launch_amp_packed(const AmpParams& p, bool in_bf16, int out_mode, bool fast, cudaStream_t st) {

@@ -40,7 +40,7 @@ struct UmmaLaunch;
 int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out);
 int conv_umma_launch(const UmmaLaunch* l, cudaStream_t st);
 size_t umma_launch_size();
-extern int amp_vec_override, amp_chunk_override, umma_mb, umma_wide_mb2, umma_max_ctas, umma_ntile_cap, umma_tap_group, umma_a_stages, umma_stack, amp_mma_enable, amp_mma_tiles, amp_packed_enable, amp_stream_enable, amp_stream_bf16_enable;
+extern int amp_vec_override, amp_chunk_override, umma_mb, umma_wide_mb2, umma_max_ctas, umma_ntile_cap, umma_tap_group, umma_a_stages, umma_stack, amp_mma_enable, amp_mma_tiles, amp_packed_enable, amp_stream_enable, amp_stream_bf16_enable, amp_ct_enable;
 
 static int conv_forward(const bvg_conv_desc* d, cudaStream_t st) {
   BVG_REQUIRE(d && d->w, "conv: null descriptor");
@@ -100,6 +100,7 @@ int bvg_set_tuning(const char* name, int value) {
   else if (!strcmp(name, "amp_packed")) bvg::amp_packed_enable = value;
   else if (!strcmp(name, "amp_stream")) bvg::amp_stream_enable = value;
   else if (!strcmp(name, "amp_stream_bf16")) bvg::amp_stream_bf16_enable = value;
+  else if (!strcmp(name, "amp_ct")) bvg::amp_ct_enable = value;
   else {
     bvg::set_error("unknown tuning knob '%s'", name);
     return BVG_EINVAL;

@@ -139,31 +139,40 @@ def test_amp_formats(ops, in_dt, out_dt):
 @pytest.mark.parametrize("fast_sin", [False, True])
 def test_amp_packed_equals_scalar(ops, in_dt, out_dt, fast_sin):
     """The FFMA2 (fma.rn.f32x2) kernel performs the scalar kernel's fp32 operations two channels at a
-    time: outputs must be bit-identical, including both replicate clamps and ragged chunk ends."""
+    time: outputs must be bit-identical, including both replicate clamps, ragged chunk ends and the clamp-free
+    fast path of interior chunks; the per-C instantiations (compile-time channel count) must equal the
+    runtime-C kernel."""
     _ops, L = ops
     rng = np.random.default_rng(11)
-    for shape in [(2, 24, 1000), (1, 768, 301), (3, 6, 97), (1, 48, 13), (1, 2, 5)]:
+    for shape in [(2, 24, 1000), (1, 768, 301), (3, 6, 97), (1, 48, 13), (1, 2, 5), (1, 96, 200), (2, 24, 95), (1, 24, 1), (1, 24, 2), (1, 24, 3), (1, 24, 7)]:
         Ch = shape[1]
         x = (rng.standard_normal(shape) * 1.5).astype(np.float32)
         a, invb = snake_params((rng.standard_normal(Ch) * 0.3).astype(np.float32), (rng.standard_normal(Ch) * 0.3).astype(np.float32), True)
         f = golden_taps()
-        L.set_tuning("amp_mma", 0)
-        L.set_tuning("amp_stream", 0)
-        try:
-            y_packed = _ops.activation1d(cl(x), a, invb, f, f, in_dtype=in_dt, out_dtype=out_dt, fast_sin=fast_sin).cpu().numpy()
-            L.set_tuning("amp_packed", 0)
-            y_scalar = _ops.activation1d(cl(x), a, invb, f, f, in_dtype=in_dt, out_dtype=out_dt, fast_sin=fast_sin).cpu().numpy()
-        finally:
-            L.set_tuning("amp_packed", 1)
-            L.set_tuning("amp_mma", 1)
+        for chunk in (0, 1):
+            L.set_tuning("amp_mma", 0)
             L.set_tuning("amp_stream", 0)
-        if fast_sin:
-            np.testing.assert_array_equal(y_packed, y_scalar)
-        else:
-            # the scalar kernel's range reduction lets nvcc contract u*a + magic into one FFMA; the packed one
-            # rounds the product first: the reduced phase can differ by one rounding (never a parity flip of sin^2)
-            tol = {L.F32: 2e-6, L.SPLIT: 2**-14, L.BF16: 2**-7}[out_dt]  # one fp32 ulp can move a bf16 / split rounding
-            np.testing.assert_allclose(y_packed, y_scalar, atol=tol * max(1.0, float(np.abs(y_scalar).max())), rtol=0)
+            L.set_tuning("amp_chunk", chunk)
+            try:
+                y_packed = _ops.activation1d(cl(x), a, invb, f, f, in_dtype=in_dt, out_dtype=out_dt, fast_sin=fast_sin).cpu().numpy()
+                L.set_tuning("amp_ct", 0)  # runtime channel count instead of the per-C instantiation
+                y_packed_rt = _ops.activation1d(cl(x), a, invb, f, f, in_dtype=in_dt, out_dtype=out_dt, fast_sin=fast_sin).cpu().numpy()
+                L.set_tuning("amp_packed", 0)
+                y_scalar = _ops.activation1d(cl(x), a, invb, f, f, in_dtype=in_dt, out_dtype=out_dt, fast_sin=fast_sin).cpu().numpy()
+            finally:
+                L.set_tuning("amp_packed", 1)
+                L.set_tuning("amp_ct", 1)
+                L.set_tuning("amp_mma", 1)
+                L.set_tuning("amp_stream", 0)
+                L.set_tuning("amp_chunk", 0)
+            np.testing.assert_array_equal(y_packed, y_packed_rt)
+            if fast_sin:
+                np.testing.assert_array_equal(y_packed, y_scalar)
+            else:
+                # the scalar kernel's range reduction lets nvcc contract u*a + magic into one FFMA; the packed one
+                # rounds the product first: the reduced phase can differ by one rounding (never a parity flip of sin^2)
+                tol = {L.F32: 2e-6, L.SPLIT: 2**-14, L.BF16: 2**-7}[out_dt]  # one fp32 ulp can move a bf16 / split rounding
+                np.testing.assert_allclose(y_packed, y_scalar, atol=tol * max(1.0, float(np.abs(y_scalar).max())), rtol=0)
 
 
 AMP_MMA_SHAPES = [(2, 24, 1000), (1, 768, 301), (3, 8, 97), (2, 40, 64), (1, 48, 2500), (2, 96, 133), (1, 16, 4), (1, 64, 259), (2, 112, 515)]
