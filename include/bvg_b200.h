@@ -138,6 +138,12 @@ typedef struct bvg_conv_geom {
   int32_t backend;     /* bvg_backend */
   int32_t split;       /* UMMA only */
   int32_t n_tile;      /* 0 = choose */
+  int32_t fold;        /* Conv1d on UMMA only; 0 / 1 = none.  P > 1: "time folding" for narrow layers -- P consecutive
+                          rows of [B, L, cin] are read as one row of [B, L/P, P*cin] (same memory, L % P == 0) and the
+                          layer becomes a Conv1d with P*cin -> P*cout channels whose taps are the block-Toeplitz
+                          arrangement of the original ones (row p_out of a block of outputs takes original tap j from
+                          input row P*shift + p_in with j*d - padding = P*shift + p_in - p_out).  The caller passes
+                          L/P as bvg_conv_desc.L; w->cin, n_total, x_pitch describe the folded layer. */
 } bvg_conv_geom;
 
 int bvg_conv_pack_bytes(const bvg_conv_geom* g, size_t* weight_plane_bytes, size_t* bias_bytes);

@@ -85,6 +85,7 @@ class ConvGeom(C.Structure):
         ("backend", C.c_int32),
         ("split", C.c_int32),
         ("n_tile", C.c_int32),
+        ("fold", C.c_int32),
     ]
 
 

@@ -34,7 +34,7 @@ __global__ void wn_scale_kernel(const float* __restrict__ v, const float* __rest
 struct PackParams {
   const float* v;
   const float* scale;
-  int transposed, cin, cout, ksize, dilation, stride, padding;
+  int transposed, cin, cout, ksize, dilation, stride, padding, fold;
   int backend, n_total, n_tile, n_tiles, cin_pad, tap_stride, stacked;
   int n_taps[BVG_MAX_NTILES];
   int shift[BVG_MAX_NTILES][BVG_MAX_TAPS];
@@ -46,7 +46,18 @@ struct PackParams {
 
 // value of the folded weight seen by output column n through the tap with input-row shift `sh`
 __device__ __forceinline__ float folded_weight(const PackParams& p, int n, int ci, int sh) {
-  if (n >= p.n_total || ci >= p.cin) return 0.f;
+  if (n >= p.n_total || ci >= p.cin * p.fold) return 0.f;
+  if (p.fold > 1) {
+    // time-folded Conv1d: output row P q + po takes x[P (q + sh) + pi] through original tap j with
+    // j d - padding = P sh + pi - po  (block-Toeplitz arrangement of the original taps)
+    const int po = n / p.cout, co = n % p.cout;
+    const int pi = ci / p.cin, c = ci % p.cin;
+    const int num = p.fold * sh + pi - po + p.padding;
+    if (num < 0 || num % p.dilation != 0) return 0.f;
+    const int j = num / p.dilation;
+    if (j >= p.ksize) return 0.f;
+    return p.scale[co] * p.v[((long long)co * p.cin + c) * p.ksize + j];
+  }
   if (!p.transposed) {
     // out[t] = sum_j w[n, ci, j] x[t - padding + j d]  =>  shift = j d - padding
     const int num = sh + p.padding;
@@ -122,10 +133,12 @@ int conv_geometry(const bvg_conv_geom* g, bvg_conv_weights* w) {
   BVG_REQUIRE(g->backend == BVG_SIMT || g->backend == BVG_UMMA, "conv geometry: bad backend");
   const bool tr = g->transposed != 0;
   BVG_REQUIRE(tr ? g->stride > 0 : g->dilation > 0, "conv geometry: bad stride/dilation");
+  const int fold = g->fold > 1 ? g->fold : 1;
+  BVG_REQUIRE(fold == 1 || (!tr && g->backend == BVG_UMMA), "conv geometry: time folding is for Conv1d on the UMMA backend");
   w->backend = g->backend;
-  w->cin = g->cin;
+  w->cin = g->cin * fold;
   w->split = (g->backend == BVG_UMMA && g->split) ? 1 : 0;
-  const int n_total = tr ? g->stride * g->cout : g->cout;
+  const int n_total = tr ? g->stride * g->cout : fold * g->cout;
   w->n_total = n_total;
 
   int n_tile;
@@ -134,8 +147,8 @@ int conv_geometry(const bvg_conv_geom* g, bvg_conv_weights* w) {
     w->cin_pad = round_up(g->cin, 4);
     w->x_pitch = round_up(g->cin, 4);
   } else {
-    w->cin_pad = round_up(g->cin, 64);
-    w->x_pitch = round_up(g->cin, 8);
+    w->cin_pad = round_up(g->cin * fold, 64);
+    w->x_pitch = round_up(g->cin * fold, 8);
     if (g->n_tile > 0) {
       n_tile = g->n_tile;
     } else {
@@ -165,7 +178,13 @@ int conv_geometry(const bvg_conv_geom* g, bvg_conv_weights* w) {
   int max_taps = 0;
   for (int t = 0; t < n_tables; ++t) {
     int nt = 0;
-    if (!tr) {
+    if (fold > 1) {
+      // super-row shifts sh with some (p_in, p_out, j):  P sh = j d - padding - (p_in - p_out),  |p_in - p_out| < P
+      const int s_lo = -floor_div(g->padding + fold - 1, fold);
+      const int s_hi = floor_div((g->ksize - 1) * g->dilation - g->padding + fold - 1, fold);
+      BVG_REQUIRE(s_hi >= s_lo && s_hi - s_lo + 1 <= BVG_MAX_TAPS, "conv geometry: folded conv needs %d taps", s_hi - s_lo + 1);
+      for (int sh = s_lo; sh <= s_hi; ++sh) w->shift[t][nt++] = sh;
+    } else if (!tr) {
       BVG_REQUIRE(g->ksize <= BVG_MAX_TAPS, "conv geometry: kernel size %d exceeds BVG_MAX_TAPS", g->ksize);
       for (int j = 0; j < g->ksize; ++j) w->shift[t][nt++] = j * g->dilation - g->padding;
     } else {
@@ -212,6 +231,7 @@ int pack_conv_weights(const bvg_conv_geom* g, const float* d_v, const float* d_g
   p.dilation = g->dilation > 0 ? g->dilation : 1;
   p.stride = g->stride > 0 ? g->stride : 1;
   p.padding = g->padding;
+  p.fold = g->fold > 1 ? g->fold : 1;
   p.backend = w->backend;
   p.n_total = w->n_total;
   p.n_tile = w->n_tile;

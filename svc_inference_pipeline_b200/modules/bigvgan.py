@@ -160,11 +160,12 @@ _NULL = L.Tensor(None, None, L.F32, 0)
 class _PackedConv:
     """Folded + packed weights of one conv layer, resident on the device."""
 
-    def __init__(self, conv: _WNConv, backend: int, split: bool, stream):
+    def __init__(self, conv: _WNConv, backend: int, split: bool, stream, fold: int = 1):
         lib = L.lib()
         dev = conv.weight_v.device
+        self.fold = int(fold) if fold and fold > 1 else 1  # time folding (include/bvg_b200.h, bvg_conv_geom.fold)
         self.geom = L.ConvGeom(
-            int(conv.transposed), conv.cin, conv.cout, conv.ksize, conv.dilation, conv.stride, conv.padding, backend, int(split), 0
+            int(conv.transposed), conv.cin, conv.cout, conv.ksize, conv.dilation, conv.stride, conv.padding, backend, int(split), 0, self.fold
         )
         wb, bb = C.c_size_t(), C.c_size_t()
         L.check(lib.bvg_conv_pack_bytes(C.byref(self.geom), C.byref(wb), C.byref(bb)), "conv_pack_bytes")
@@ -255,6 +256,8 @@ class Generator(nn.Module):
         self._packed = None
         self._programs: "OrderedDict[tuple, _Program]" = OrderedDict()
         self.max_cached_programs = 6
+        # narrow resblock convolutions read four rows as one (see _time_fold); set False + _invalidate() to compare
+        self.time_fold = True
         self.use_cuda_graph = False
         # Two half-batches on two streams, launched op by op in alternation: the tensor-core convolutions of
         # one half (one persistent CTA per SM, ~6 % of the issue slots) share the SMs with the FFMA-bound
@@ -355,7 +358,7 @@ class Generator(nn.Module):
                             f"layer {name} ({m.cin}->{m.cout}) cannot run on the tensor-core path "
                             "(channel counts must be multiples of 8); use precision='fp32_simt'"
                         )
-                    packed["conv"][name] = _PackedConv(m, be, split, stream)
+                    packed["conv"][name] = _PackedConv(m, be, split, stream, fold=self._time_fold(name, m, be))
                 elif isinstance(m, _Activation1d):
                     packed["act"][name] = self._act_params(m)
             cp = self.conv_post
@@ -368,6 +371,26 @@ class Generator(nn.Module):
             packed["post_bias"] = float(cp.bias.detach().float().cpu()[0])
             torch.cuda.current_stream(dev).synchronize()
         self._packed = packed
+
+    def _time_fold(self, name: str, m: _WNConv, backend: int) -> int:
+        """Rows folded into channels for the narrowest resblock convolutions (``bvg_conv_geom.fold``).  A C = 24
+        layer is bound by the tensor core re-reading its 128-row activation tile from shared memory for every tap
+        (a 24-column MMA reads 4 KB for 16 cycles of math) and by per-tile overheads; read as [L/4, 96] the same
+        layer is a 96 -> 96 conv with about (k - 1) d / 4 + 2 taps on a quarter of the rows.  Measured on B200
+        (gpurun_out/ab_fold.txt, ab_fold2.txt): k = 7 / 11 at dilation 1 run 25-38 % faster, dilated and 3-tap layers
+        0-5 %; folding C = 48 by 2 or C = 96 by 2 is slower, so only C <= 24 folds."""
+        if not self.time_fold or backend != L.UMMA or m.transposed or not name.startswith("resblocks."):
+            return 1
+        fold = 4
+        if m.cin != m.cout or m.cin > 24 or m.cin % 8 != 0:
+            return 1
+        if ((m.ksize - 1) * m.dilation + 2 * (fold - 1)) // fold + 2 > 16:  # BVG_MAX_TAPS
+            return 1
+        stage = int(name.split(".")[1]) // self.num_kernels
+        up = 1
+        for r in self.cfg.upsample_rates[: stage + 1]:
+            up *= int(r)
+        return fold if up % fold == 0 else 1
 
     def _umma_ok(self, m: _WNConv) -> bool:
         if m is self.conv_pre:
@@ -404,7 +427,9 @@ class Generator(nn.Module):
             d.x, d.out = x.tensor(), out.tensor()
             d.res = res.tensor() if res is not None else _NULL
             d.acc_in = acc.tensor() if acc is not None else _NULL
-            d.div, d.B, d.L = float(div), B_, L_
+            fold = pk["conv"][name].fold
+            assert L_ % fold == 0
+            d.div, d.B, d.L = float(div), B_, L_ // fold
             d.w = C.pointer(pk["conv"][name].desc)
             ops.append(op)
 

@@ -59,7 +59,7 @@ def activation1d(x, a, invb, taps_up, taps_down, in_dtype=L.F32, out_dtype=L.F32
     return from_buf(yb, x.shape)
 
 
-def pack_conv(v, g, bias, *, transposed=False, dilation=1, stride=1, padding=0, backend=L.UMMA, split=False) -> _PackedConv:
+def pack_conv(v, g, bias, *, transposed=False, dilation=1, stride=1, padding=0, backend=L.UMMA, split=False, fold=1) -> _PackedConv:
     """Fold + pack a weight-normed conv given reference-layout ``weight_v`` / ``weight_g`` / ``bias``."""
     if transposed:
         cin, cout, k = v.shape
@@ -72,7 +72,7 @@ def pack_conv(v, g, bias, *, transposed=False, dilation=1, stride=1, padding=0, 
         holder.bias.copy_(bias)
     holder = holder.to(v.device)
     with torch.cuda.device(v.device):
-        pc = _PackedConv(holder, backend, split, _stream(v.device))
+        pc = _PackedConv(holder, backend, split, _stream(v.device), fold=fold)
     pc._holder = holder
     return pc
 

@@ -260,3 +260,35 @@ def test_overlapped_forward_is_identical(repo_model, B):
         repo_model.overlap_streams = True
     assert y_ov.shape == (B, 1, 53 * 256)
     assert torch.equal(y_ov, y_plain) and torch.equal(y_ov, y_ov2)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_time_folded_layers_match_unfolded(repo_model, precision):
+    """The C = 24 resblock convolutions run time-folded (four rows read as one row of 96 channels,
+    bvg_conv_geom.fold): same waveform as the unfolded layers up to accumulation order."""
+    from svc_inference_pipeline_b200.utils import synth
+
+    m = repo_model
+    old = m.precision
+    mel = torch.from_numpy(synth.synthetic_mel(2, 100, 40, 91)).cuda()
+    try:
+        m.set_precision(precision)
+        m.time_fold = True
+        m._invalidate()
+        y_fold = m(mel).clone()
+        folded = [n for n, pc in m._packed["conv"].items() if pc.fold > 1]
+        m.time_fold = False
+        m._invalidate()
+        y_plain = m(mel).clone()
+        assert not [n for n, pc in m._packed["conv"].items() if pc.fold > 1]
+    finally:
+        m.time_fold = True
+        m.set_precision(old)
+        m._invalidate()
+    assert len(folded) == 18, folded  # resblocks 15-17
+    err = float((y_fold - y_plain).abs().max())
+    if precision == "fp32":
+        assert err < 2e-6, err
+    else:
+        snr = 10 * np.log10(float((y_plain.double() ** 2).sum() / ((y_fold - y_plain).double() ** 2).sum()))
+        assert snr > 45, snr

@@ -336,6 +336,52 @@ def test_conv_umma_split(ops, case, mb):
     _umma_conv_check(ops, *case, split=True, mb=mb)
 
 
+FOLD_CASES = [
+    # (B, C, L, k, d, fold)
+    (2, 24, 1000, 11, 1, 4),
+    (1, 24, 516, 7, 1, 4),
+    (3, 24, 64, 3, 1, 4),
+    (1, 24, 2048, 11, 3, 4),
+    (2, 24, 400, 7, 5, 4),
+    (2, 48, 334, 11, 1, 2),
+    (1, 48, 600, 7, 1, 2),
+    (1, 8, 96, 11, 1, 8),
+    (1, 24, 4, 11, 1, 4),
+    (1, 24, 8, 7, 1, 4),
+]
+
+
+@pytest.mark.parametrize("case", FOLD_CASES)
+@pytest.mark.parametrize("split", [False, True])
+def test_conv_umma_time_fold(ops, case, split):
+    """bvg_conv_geom.fold: P rows read as one row of P*C channels and the taps rearranged block-Toeplitz give the
+    same Conv1d -- against the fp64 oracle on the unfolded layer (zero padding at both ends, batch items kept apart,
+    dilations whose folded form has all-zero blocks) and against the unfolded tensor-core layer itself."""
+    _ops, L = ops
+    B, Ch, Ln, k, d, fold = case
+    rng = np.random.default_rng(300 + Ch + k + d + Ln)
+    x = rng.standard_normal((B, Ch, Ln)).astype(np.float32)
+    v = (rng.standard_normal((Ch, Ch, k)) / np.sqrt(Ch * k)).astype(np.float32)
+    g = (np.sqrt((v.astype(np.float64) ** 2).sum(axis=(1, 2), keepdims=True)) * rng.uniform(0.7, 1.4, (Ch, 1, 1))).astype(np.float32)
+    b = (rng.standard_normal(Ch) * 0.1).astype(np.float32)
+    wts = [torch.from_numpy(t).to(DEV) for t in (v, g, b)]
+    pc_f = _ops.pack_conv(*wts, dilation=d, padding=O.get_padding(k, d), backend=L.UMMA, split=split, fold=fold)
+    pc_u = _ops.pack_conv(*wts, dilation=d, padding=O.get_padding(k, d), backend=L.UMMA, split=split)
+    assert pc_f.x_pitch == fold * Ch and pc_f.n_total == fold * Ch
+    xl = cl(x)                                             # [B, L, C]
+    y_f = _ops.conv(xl.reshape(B, Ln // fold, fold * Ch), pc_f).reshape(B, Ln, Ch)
+    y_u = _ops.conv(xl, pc_u)
+    ref, _ = _oracle_conv(x, v, g, b, False, k, d=d)
+    yf, yu = cf(y_f), cf(y_u)
+    scale = max(1.0, np.abs(ref).max())
+    if split:
+        assert np.abs(yf - ref).max() < 3e-5 * scale
+        assert np.abs(yf - yu).max() < 3e-5 * scale
+    else:
+        assert np.abs(yf - ref).max() < 0.05 * scale
+        assert np.abs(yf - yu).max() < 2e-3  # same bf16 operands, different accumulation order
+
+
 def test_conv_umma_large_rows(ops):
     """Many tiles per CTA (pipeline wrap-around of every barrier ring) and ragged last tiles."""
     _umma_conv_check(ops, 4, 48, 20011, 7, 3, split=False, mb=0)
