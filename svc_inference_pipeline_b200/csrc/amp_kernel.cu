@@ -305,6 +305,15 @@ __device__ __forceinline__ void amp_block6_p2(const AmpParams& p, const P2 (&xa)
     const long long row0 = base + (long long)(tau0 + 6) * Cc;
 #pragma unroll
     for (int j = 0; j < 6; ++j) xb[j] = load_row2<IN_BF16>(p.x, row0 + j * Cc);
+    // L1 prefetch of the rows two blocks ahead (12 rows past the ones just requested): holds no registers, and
+    // the demand loads two blocks later hit on chip.  ncu before: 5.9 stall cycles per issue on the global loads
+    // (long scoreboard) at 24 resident warps; measured in-program +5..17 % (gpurun_out/ab_pf.txt; 6, 18, 24, 36 rows
+    // or an L2-only prefetch are behind).  Past the end of the tensor the prefetch is a dropped hint.
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const char* a = reinterpret_cast<const char*>(p.x) + (row0 + (long long)(12 + j) * Cc) * (IN_BF16 ? 2 : 4);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+    }
   } else {
 #pragma unroll
     for (int j = 0; j < 6; ++j) {

@@ -263,6 +263,7 @@ class Generator(nn.Module):
         # one half (one persistent CTA per SM, ~6 % of the issue slots) share the SMs with the FFMA-bound
         # Activation1d kernels of the other half.  Needs >= 2 utterances; results are identical.
         self.overlap_streams = True
+        self.overlap_parts = 2
         self._side_streams = None
         self._mel_denorm = None  # (range, min) device tensors when forward() takes mels normalised to [-1, 1]
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
@@ -623,21 +624,22 @@ class Generator(nn.Module):
 
     def _forward_overlapped(self, x: torch.Tensor, dev) -> torch.Tensor:
         B, _, T = x.shape
-        b0 = (B + 1) // 2
-        parts = [(0, b0), (b0, B)]
+        n = max(2, min(int(self.overlap_parts), B))
+        cuts = [(B * k + n - 1) // n for k in range(n + 1)]
+        parts = [(cuts[k], cuts[k + 1]) for k in range(n)]
         with torch.cuda.device(dev):
             progs = [self._program(hi - lo, T, slot=k) for k, (lo, hi) in enumerate(parts)]
-            if self._side_streams is None or self._side_streams[0].device != dev:
-                self._side_streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+            if self._side_streams is None or len(self._side_streams) != n or self._side_streams[0].device != dev:
+                self._side_streams = [torch.cuda.Stream(device=dev) for _ in range(n)]
             cur = torch.cuda.current_stream(dev)
             for prog, (lo, hi) in zip(progs, parts):
                 prog.mel_in.copy_(x[lo:hi], non_blocking=True)
             ready = cur.record_event()
             for st in self._side_streams:
                 st.wait_event(ready)
-            handles = (C.c_void_p * 2)(progs[0].handle, progs[1].handle)
-            streams = (C.c_void_p * 2)(self._side_streams[0].cuda_stream, self._side_streams[1].cuda_stream)
-            L.check(L.lib().bvg_program_run_interleaved(handles, streams, 2), "program_run_interleaved")
+            handles = (C.c_void_p * n)(*[pr.handle for pr in progs])
+            streams = (C.c_void_p * n)(*[st.cuda_stream for st in self._side_streams])
+            L.check(L.lib().bvg_program_run_interleaved(handles, streams, n), "program_run_interleaved")
             for st in self._side_streams:
                 cur.wait_event(st.record_event())
-            return torch.cat([progs[0].out, progs[1].out], dim=0)
+            return torch.cat([pr.out for pr in progs], dim=0)

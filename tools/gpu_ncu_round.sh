@@ -19,4 +19,10 @@ ncu --set full --clock-control none --import-source on -k regex:conv_umma -s 224
 echo "narrow conv rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:amp_kernel -s 127 -c 1 -o $OUT/prof_amp_s1_$TAG -f python tools/ncu_target.py fp32 > $OUT/ncu_c_$TAG.log 2>&1
 echo "amp rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:amp_kernel -s 199 -c 1 -o $OUT/prof_amp_s5_$TAG -f python tools/ncu_target.py fp32 > $OUT/ncu_d_$TAG.log 2>&1
+echo "amp C=24 rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:amp_mma -s 127 -c 1 -o $OUT/prof_ampmma_s1_bf16_$TAG -f python tools/ncu_target.py bf16 > $OUT/ncu_e_$TAG.log 2>&1
+echo "amp_mma bf16 rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:conv_umma -s 148 -c 1 -o $OUT/prof_conv_s1k11_$TAG -f python tools/ncu_target.py fp32 > $OUT/ncu_f_$TAG.log 2>&1
+echo "stage-1 conv rc=$?"
 ls -la $OUT | tail -12
