@@ -43,7 +43,7 @@ AMP_ELEMS_PER_FRAME = 614_400  # Activation1d elements per mel frame over the 10
 
 def load_traffic(precision, kernel):
     """DRAM bytes per launch of a kernel class from the committed ncu launch list (None if absent)."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic_v7.json")
+    path = os.path.join(ROOT, "profiles", "r01_traffic_v14.json")
     try:
         return json.load(open(path))[precision][kernel]["dram_bytes_per_launch"]
     except Exception:
@@ -271,7 +271,7 @@ def main():
                 "issued_tflops": conv_tflops * (3 if args.precision == "fp32" else 1), "issued_frac": conv_tflops * (3 if args.precision == "fp32" else 1) / peaks["tensor"],
                 "peak_source": peaks["src"], "avg_launch_ms": prof["conv_ms"] / max(1, prof["conv_n"]), "share_of_step": prof["conv_ms"] / prof["total_ms"],
                 "note": "algorithmic FLOPs 2*Cin*Cout*K*L per conv (1.8041 GFLOP/frame); the fp32 path issues 3 bf16 MMAs per product (hi*hi + lo*hi + hi*lo), "
-                        "counted once in achieved/frac and three times in issued_*; ncu: 98 % tensor-pipe active on the C>=384 layers (profiles/r01_ncu_summary_v7.md); "
+                        "counted once in achieved/frac and three times in issued_*; ncu: 97 % / 86 % tensor-pipe active on the C=768 / C=384 layers (profiles/r01_ncu_summary_v14.md); "
                         "traffic = mean DRAM bytes per launch from the committed ncu launch list"}
     roofline_amp = {"bound": "hbm", "kernel": "amp_kernel_p2 / amp_mma_kernel (109 launches/step)", "achieved": amp_gbs, "peak": peaks["hbm"], "unit": "GB/s",
                     "frac": amp_gbs / peaks["hbm"], "traffic": load_traffic("bf16" if args.precision == "bf16" else "fp32", "amp_kernel"), "avg_launch_ms": prof["amp_ms"] / max(1, prof["amp_n"]),
