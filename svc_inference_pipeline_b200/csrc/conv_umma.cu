@@ -660,7 +660,11 @@ struct UmmaLaunch {
 };
 
 int umma_mb = 0;         // tuning/test hook: force M blocks per tile (0 = choose)
-int umma_wide_mb2 = 0;   // tuning/test hook: allow mb = 2 with a single TMEM stage for 256-column tiles
+// mb = 2 with a single TMEM stage (2 x 256 columns): 0 = for SPLIT operands only (three MMA passes make a tile
+// three times longer, so the un-overlapped epilogue costs ~1 % while every weight box feeds two row blocks:
+// stage-0 convolutions 19.2 -> 17.9 ms per forward, gpurun_out/ab_mb2_fp32.txt; bf16 operands lose 13 %),
+// 1 = for every tile that fits (also 192 columns), -1 = never
+int umma_wide_mb2 = 0;
 int umma_max_ctas = 0;   // tuning/test hook: cap the persistent grid
 int umma_tap_group = 0;  // tuning/test hook: taps per weight stage (0 = choose)
 int umma_a_stages = 0;   // tuning/test hook: activation stages (0 = choose)
@@ -747,7 +751,9 @@ int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out) {
   int mb = 1;
   for (int cand = UM_MAX_MB; cand >= 1; cand >>= 1) {
     int br, nb, tg;
-    const bool tmem_ok = cand * p.col_stride * 2 <= 512 || (cand == 1) || (umma_wide_mb2 && cand == 2 && cand * p.col_stride <= 512);
+    const bool single_stage_ok = cand == 2 && cand * p.col_stride <= 512 &&
+                                 (umma_wide_mb2 > 0 || (umma_wide_mb2 == 0 && planes == 2 && p.col_stride == 256));
+    const bool tmem_ok = cand * p.col_stride * 2 <= 512 || (cand == 1) || single_stage_ok;
     if (!tmem_ok) continue;
     if (plan_smem(cand, 2, max_span, planes, w_rows, max_taps, &br, &nb, &tg) < (cand == 1 ? 2 : 3)) continue;
     const long long tiles = (long long)d->B * ceil_div(d->L, cand * UM_BM) * w->n_tiles;

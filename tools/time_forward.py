@@ -12,16 +12,25 @@ ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--frames", type=int, default=938)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--precisions", default="fp32,bf16")
+ap.add_argument("--v2", action="store_true", help="BASELINE configs[4]: 512x generator (input_dim 128, rates 8,4,2,2,2,2), hop 512 at 44.1 kHz; "
+                                                  "one rank's share of B64 x 30 s on 8 GPUs is --batch 8 --frames 2584")
+ap.add_argument("--parts", default="0,2", help="overlap settings to time (0 = one stream, n = n batch parts on n streams)")
 a = ap.parse_args()
 cfg = load_config(os.path.join(ROOT, "svc_inference_pipeline_b200", "config", "config.json"))
-m = Generator(cfg.vocoder)
-m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.synthetic_state_dict({k: cfg.vocoder[k] for k in cfg.vocoder.keys()}, 0).items()})
+vc = {k: cfg.vocoder[k] for k in cfg.vocoder.keys()}
+hop, fs = 256, 24000
+if a.v2:
+    vc.update(input_dim=128, upsample_rates=[8, 4, 2, 2, 2, 2], upsample_kernel_sizes=[16, 8, 4, 4, 4, 4])
+    hop, fs = 512, 44100
+from svc_inference_pipeline_b200.utils.util import JsonHParams
+m = Generator(JsonHParams(**vc))
+m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.synthetic_state_dict(vc, 0).items()})
 m = m.cuda().eval()
-mel = torch.from_numpy(synth.synthetic_mel(a.batch, 100, a.frames, 1235)).cuda()
+mel = torch.from_numpy(synth.synthetic_mel(a.batch, vc["input_dim"], a.frames, 1235)).cuda()
 for prec in a.precisions.split(","):
     m.set_precision(prec)
     outs = {}
-    for ov in (False, 2, 3, 4, False, 2, 3, 4):
+    for ov in [int(t) for t in a.parts.split(",")] * 2:
         m.overlap_streams = bool(ov)
         m.overlap_parts = ov or 2
         for _ in range(3):
@@ -35,5 +44,6 @@ for prec in a.precisions.split(","):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / a.reps
         outs[ov] = y
-        print(f"{prec} overlap={ov}: {ms:.2f} ms/step, {a.batch * a.frames * 256 / 24000 / (ms / 1e3):.0f} audio-s/s", flush=True)
-    print(f"{prec} max |overlap - plain| = {max(float((outs[k] - outs[False]).abs().max()) for k in (2, 3, 4)):.3e}")
+        print(f"{prec} overlap={ov}: {ms:.2f} ms/step, {a.batch * a.frames * hop / fs / (ms / 1e3):.0f} audio-s/s", flush=True)
+    if len(outs) > 1:
+        print(f"{prec} max |overlap - plain| = {max(float((outs[k] - outs[0]).abs().max()) for k in outs if k):.3e}")
