@@ -119,6 +119,10 @@ typedef struct bvg_conv_desc {
   float div;           /* out /= div when != 1 (the xs / num_kernels of modules/bigvgan.py:615) */
   int32_t B, L;
   const bvg_conv_weights* w;
+  const struct bvg_amp_desc* pre_amp; /* optional (UMMA, 8 <= Cin <= 64): fuse this Activation1d in front of the convolution --
+                                         the kernel computes its operand from pre_amp->x (F32 [B, L, Cin]) and x above is
+                                         ignored; pre_amp->y is not written.  The AMP-into-conv fusion of the narrow stages:
+                                         modules/bigvgan.py:428-431  xt = c1(a1(x)); xt = c2(a2(xt)) */
 } bvg_conv_desc;
 
 int bvg_conv_fwd(const bvg_conv_desc* d, void* stream);

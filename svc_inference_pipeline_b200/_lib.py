@@ -70,6 +70,7 @@ class ConvDesc(C.Structure):
         ("B", C.c_int32),
         ("L", C.c_int32),
         ("w", C.POINTER(ConvWeights)),
+        ("pre_amp", C.c_void_p),  # const bvg_amp_desc*: Activation1d fused in front of the convolution (or NULL)
     ]
 
 

@@ -16,7 +16,7 @@
 // row.  Steps are processed in blocks of 6 with two register sets used ping-pong, so the
 // windows rotate with compile-time indices and no register moves.  A warp covers 32*VEC
 // adjacent channels of one row => every global access is a fully coalesced row segment.
-#include "common.cuh"
+#include "amp_p2.cuh"
 
 namespace bvg {
 
@@ -98,23 +98,6 @@ __device__ __forceinline__ void store_row(void* y, void* y_lo, long long off, co
     store_bf16_row<VEC>(y, off, hi);
     store_bf16_row<VEC>(y_lo, off, lo);
   }
-}
-
-// sin(a*u): FAST = MUFU on the raw product (phase error ~|a*u| * 1e-7, like the reference's own
-// fp32 rounding of a*u); otherwise reduce exactly to [-pi/2, pi/2] first (sin^2 has period pi),
-// which keeps MUFU.SIN in its most accurate range (abs err 2^-21).  apar = a (FAST) or a/pi.
-template <bool FAST_SIN>
-__device__ __forceinline__ float snake_one(float u, float apar, float invb) {
-  float s;
-  if constexpr (FAST_SIN) {
-    s = __sinf(u * apar);
-  } else {
-    float t = u * apar;               // half-turns
-    float k = (t + 12582912.0f) - 12582912.0f;  // rint for |t| < 2^22
-    float r = t - k;                  // [-0.5, 0.5]
-    s = __sinf(r * 3.14159265358979f);
-  }
-  return fmaf(invb, s * s, u);
 }
 
 template <bool IN_BF16, int OUT_MODE, int VEC, bool FAST_SIN, bool STORE>
@@ -239,30 +222,6 @@ __global__ void __launch_bounds__(128) amp_kernel(const __grid_constant__ AmpPar
 // Each lane of an f32x2 operation is an IEEE fp32 operation, so results are bit-identical to the
 // scalar kernel above.
 // ------------------------------------------------------------------------------------------------
-typedef unsigned long long P2;  // two packed fp32 (channel c in the low half, c+1 in the high half)
-
-__device__ __forceinline__ P2 pk2(float a, float b) {
-  P2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void upk2(P2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ P2 fma2(P2 a, P2 b, P2 c) {
-  P2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ P2 mul2(P2 a, P2 b) {
-  P2 d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ P2 add2(P2 a, P2 b) {
-  P2 d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-
 template <bool IN_BF16>
 __device__ __forceinline__ P2 load_row2(const void* base, long long off) {
   // plain (coherent) loads, not ld.global.nc: a load that may alias the output rows stays behind the stores
@@ -274,22 +233,6 @@ __device__ __forceinline__ P2 load_row2(const void* base, long long off) {
     const uint32_t t = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(base) + off);
     return pk2(__uint_as_float(t << 16), __uint_as_float(t & 0xffff0000u));
   }
-}
-
-// same operation order as snake_one, two channels at a time (apar = a or a/pi, see snake_one)
-template <bool FAST_SIN>
-__device__ __forceinline__ P2 snake_two(P2 u, P2 apar, P2 invb) {
-  P2 arg = mul2(u, apar);
-  if constexpr (!FAST_SIN) {
-    const P2 magic = pk2(12582912.0f, 12582912.0f), nmagic = pk2(-12582912.0f, -12582912.0f);
-    const P2 k = add2(add2(arg, magic), nmagic);              // rint for |t| < 2^22
-    arg = fma2(k, pk2(-1.0f, -1.0f), arg);                     // [-0.5, 0.5] half-turns (exact)
-    arg = mul2(arg, pk2(3.14159265358979f, 3.14159265358979f));
-  }
-  float a0, a1;
-  upk2(arg, a0, a1);
-  const P2 s = pk2(__sinf(a0), __sinf(a1));
-  return fma2(invb, mul2(s, s), u);
 }
 
 // INTERIOR: the block touches no sequence end (rows tau0+6 .. tau0+11 exist, tau0+5 < L-3): no clamps, no

@@ -44,6 +44,7 @@ extern int amp_vec_override, amp_chunk_override, umma_mb, umma_wide_mb2, umma_ma
 
 static int conv_forward(const bvg_conv_desc* d, cudaStream_t st) {
   BVG_REQUIRE(d && d->w, "conv: null descriptor");
+  BVG_REQUIRE(!d->pre_amp || d->w->backend == BVG_UMMA, "conv: a fused Activation1d (pre_amp) needs the UMMA backend");
   if (d->w->backend == BVG_SIMT) return conv_simt_forward(d, st);
   if (d->w->backend == BVG_UMMA) return conv_umma_forward(d, st);
   set_error("conv: unknown backend %d", d->w->backend);
@@ -163,6 +164,11 @@ int bvg_program_create(const bvg_op* ops, int32_t n_ops, bvg_program** out) {
       bvg_conv_weights* w = new bvg_conv_weights(*op.u.conv.w);
       p->owned_weights.push_back(w);
       op.u.conv.w = w;
+      if (w->backend != BVG_UMMA && op.u.conv.pre_amp) {
+        bvg::set_error("program_create: op %d fuses an Activation1d into a convolution that is not on the UMMA backend", i);
+        delete p;
+        return BVG_EINVAL;
+      }
       if (w->backend == BVG_UMMA) {
         void* rec = ::operator new(bvg::umma_launch_size());
         p->umma[i] = rec;

@@ -27,6 +27,7 @@
 
 #include <cstring>
 
+#include "amp_p2.cuh"
 #include "common.cuh"
 #include "epilogue.cuh"
 
@@ -36,6 +37,8 @@ constexpr int UM_BM = 128;          // rows per M block (TMEM lanes)
 constexpr int UM_KB = 64;           // channels per K slice (one 128-byte swizzle row of bf16)
 constexpr int UM_EPI_WARPS = 8;     // two warps per TMEM lane quarter
 constexpr int UM_THREADS = 128 + 32 * UM_EPI_WARPS;
+constexpr int UM_AMP_WARPS = 8;      // fused mode: Activation1d producer warps after the epilogue warps
+constexpr int UM_THREADS_FUSED = UM_THREADS + 32 * UM_AMP_WARPS;
 constexpr int UM_MAX_A_STAGES = 4;   // activation super-tile stages (2..4, chosen per launch)
 constexpr int UM_MAX_B_STAGES = 8;
 constexpr int UM_MAX_T_STAGES = 4;
@@ -71,6 +74,15 @@ struct UmmaParams {
   int min_shift[BVG_MAX_NTILES];
   int shift[BVG_MAX_NTILES][BVG_MAX_TAPS];
   int* err_flag;        // optional device word set before a watchdog trap
+  // fused Activation1d producer (bvg_conv_desc.pre_amp): the A operand is computed here from the Activation1d's
+  // fp32 input instead of being loaded by TMA
+  const float* f_x;     // [B, L, f_C] fp32, channels-last
+  const float* f_a;
+  const float* f_invb;
+  float f_gu[12], f_fd[12];
+  int f_C;
+  int f_need;           // rows of an A stage the MMAs read: tile_rows + max shift - min shift
+  int f_fast_sin;
 };
 
 namespace ptx {
@@ -246,13 +258,190 @@ __device__ __forceinline__ int issue_stage(const UmmaParams& p, const int* __res
   return sh;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused Activation1d producer (bvg_conv_desc.pre_amp): warps 12-19 compute the A operand of
+// the convolution -- z = DownSample1d(snake(UpSample1d(x))) of reference modules/bigvgan.py:251-256 -- from the
+// Activation1d's fp32 input and write the (hi, lo) bf16 planes straight into the 128-byte-swizzled A stages the
+// UMMA descriptors read, so the activated tensor never exists in HBM (saves its 4-byte write and 4-byte read per
+// element and the separate kernel) and the FFMA work runs under the tile's MMAs.  Arithmetic and operation order
+// are amp_kernel_p2's (amp_kernel.cu); a thread owns one channel pair and a run of consecutive rows of the
+// tile, rows outside [0, L) are the convolution's zero padding.  Narrow layers only (Cin <= 64 * a_stages): all
+// Cin slices of a tile are produced together.
+// ------------------------------------------------------------------------------------------------
+template <bool FAST_SIN>
+__device__ __forceinline__ void fused_block6(const UmmaParams& p, const P2 (&xa)[6], P2 (&xb)[6], const P2 (&sa)[12], P2 (&sb)[12], int tau0,
+                                             const float* __restrict__ xcol, int t_lo, int t_hi, int trow0, uint32_t pair_base, P2 apar, P2 invb,
+                                             bool store) {
+  const int L = p.L, C = p.f_C;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const int r = min(max(tau0 + 6 + j, 0), L - 1);
+    const float2 t = *reinterpret_cast<const float2*>(xcol + (long long)r * C);
+    xb[j] = pk2(t.x, t.y);
+  }
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    P2 pa = 0ull, pb = 0ull;
+#pragma unroll
+    for (int m = 0; m < 6; ++m) {
+      const int w = j + 5 - m;
+      const P2 xv = (w < 6) ? xa[w < 6 ? w : 0] : xb[w >= 6 ? w - 6 : 0];
+      pb = fma2(pk2(p.f_gu[2 * m + 1], p.f_gu[2 * m + 1]), xv, pb);
+      pa = fma2(pk2(p.f_gu[2 * m], p.f_gu[2 * m]), xv, pa);
+    }
+    pa = snake_two<FAST_SIN>(pa, apar, invb);
+    pb = snake_two<FAST_SIN>(pb, apar, invb);
+    const int tau = tau0 + j;
+    if (tau >= L - 3) {  // right replicate clamp of the activated signal: s[j > 2L-1] = s[2L-1]
+      const P2 prev = (j == 0) ? sa[11] : sb[j == 0 ? 0 : 2 * j - 1];
+      if (tau >= L - 2) pa = prev;
+      pb = pa;
+    }
+    sb[2 * j] = pa;
+    sb[2 * j + 1] = pb;
+    if (store) {
+      P2 z = 0ull;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        const int i = 2 * j + 2 + k;
+        const P2 sv = (i < 12) ? sa[i < 12 ? i : 0] : sb[i >= 12 ? i - 12 : 0];
+        z = fma2(pk2(p.f_fd[k], p.f_fd[k]), sv, z);
+      }
+      if (tau >= t_lo && tau < t_hi) {
+        float z0, z1;
+        upk2(z, z0, z1);
+        const uint32_t hi = pack_bf16x2(z0, z1);
+        const uint32_t row = (uint32_t)(tau - trow0);
+        const uint32_t addr = (pair_base + row * 128u) ^ ((row & 7u) << 4);
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(hi) : "memory");
+        if (p.planes == 2) {
+          const P2 lo = fma2(pk2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u)), pk2(-1.0f, -1.0f), z);
+          float l0, l1;
+          upk2(lo, l0, l1);
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr + (uint32_t)p.a_plane_bytes), "r"(pack_bf16x2(l0, l1)) : "memory");
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void fused_amp_producer(const UmmaParams& p, uint32_t a_base, uint32_t bar_base) {
+  const int ptid = (int)threadIdx.x - UM_THREADS;  // 0 .. 255
+  const int lane = threadIdx.x & 31;
+  const int C = p.f_C, L = p.L;
+  const int pairs = C >> 1;
+  const int n_sub = (32 * UM_AMP_WARPS) / pairs;  // row runs per tile
+  const int pi = ptid % pairs, sub = ptid / pairs;
+  const bool active = sub < n_sub;
+  const int need = p.f_need;
+  const int rps = (need + n_sub - 1) / n_sub;
+  const int r0 = sub * rps, r1 = min(r0 + rps, need);
+  const int c = 2 * pi;
+  const int cb_mine = c >> 6;
+  const uint32_t col_bytes = (uint32_t)((c & 63) * 2);
+  const float a0 = __ldg(p.f_a + c), a1 = __ldg(p.f_a + c + 1);
+  const bool fast = p.f_fast_sin != 0;
+  const P2 apar = fast ? pk2(a0, a1) : pk2(a0 * 0.318309886183790672f, a1 * 0.318309886183790672f);
+  const P2 invb = pk2(__ldg(p.f_invb + c), __ldg(p.f_invb + c + 1));
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (UM_MAX_A_STAGES + s); };
+
+  int sa = 0, pa = 0;
+  for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const int nt = (int)(tile % p.n_tiles);
+    const long long mt = tile / p.n_tiles;
+    const int b = (int)(mt / p.m_tiles_per_item);
+    const int t0 = (int)(mt % p.m_tiles_per_item) * p.tile_rows;
+    const int trow0 = t0 + p.min_shift[nt];  // time of stage row 0
+    // stages of this tile's Cin slices (n_cb <= a_stages): wait until the MMAs of their previous use retired
+    uint32_t my_stage = 0;
+    {
+      int s = sa, par = pa;
+      for (int cb = 0; cb < p.n_cb; ++cb) {
+        ptx::mbar_wait(a_empty(s), par ^ 1, p.err_flag, 7);
+        if (cb == cb_mine) my_stage = a_base + (uint32_t)(s * p.a_stage_bytes);
+        if (++s == p.a_stages) { s = 0; par ^= 1; }
+      }
+    }
+    // channels [C, round_up(C, 16)) of the last slice are read by its last K step: zero them (TMA's out-of-bounds fill)
+    if (C & 15) {
+      int s_last = sa + p.n_cb - 1;
+      if (s_last >= p.a_stages) s_last -= p.a_stages;
+      const uint32_t base = a_base + (uint32_t)(s_last * p.a_stage_bytes) + (uint32_t)((C & 63) * 2);
+      for (int r = ptid; r < need; r += 32 * UM_AMP_WARPS) {
+        const uint32_t addr = (base + (uint32_t)r * 128u) ^ (((uint32_t)r & 7u) << 4);
+        for (int pl = 0; pl < p.planes; ++pl)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(addr + (uint32_t)(pl * p.a_plane_bytes)), "r"(0u) : "memory");
+      }
+    }
+    if (active && r0 < r1) {
+      const uint32_t pair_base = my_stage + col_bytes;
+      const int T0 = trow0 + r0, T1 = trow0 + r1;
+      const int ta = max(T0, 0), tb = min(T1, L);
+      // rows outside the sequence: Conv1d's zero padding
+      for (int t = T0; t < T1; ++t) {
+        if (t >= ta && t < tb) continue;
+        const uint32_t row = (uint32_t)(t - trow0);
+        const uint32_t addr = (pair_base + row * 128u) ^ ((row & 7u) << 4);
+        for (int pl = 0; pl < p.planes; ++pl) asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr + (uint32_t)(pl * p.a_plane_bytes)), "r"(0u) : "memory");
+      }
+      if (ta < tb) {
+        const float* xcol = p.f_x + (long long)b * L * C + c;
+        P2 xa[6], xb[6], sa_w[12], sb_w[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) sa_w[k] = 0ull;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const int r = min(max(ta - 6 + k, 0), L - 1);
+          const float2 t = *reinterpret_cast<const float2*>(xcol + (long long)r * C);
+          xa[k] = pk2(t.x, t.y);
+        }
+#define BVG_FBLOCK(XA, XB, SA, SB, TAU, STORE)                                                                  \
+  if (fast) fused_block6<true>(p, XA, XB, SA, SB, TAU, xcol, ta, tb, trow0, pair_base, apar, invb, STORE);     \
+  else fused_block6<false>(p, XA, XB, SA, SB, TAU, xcol, ta, tb, trow0, pair_base, apar, invb, STORE)
+        BVG_FBLOCK(xa, xb, sa_w, sb_w, ta - 6, false);  // warm-up: fills the s window, no output
+        // left replicate clamp of the activated signal: s[j < 0] = s[0].  The window holds s[2 ta - 7 + k]; a run may
+        // start at any row here (amp_kernel_p2's chunks start at 0 or far from it), so s[0] sits in slot 7 - 2 ta
+        if (ta == 0) {
+#pragma unroll
+          for (int k = 0; k < 7; ++k) sb_w[k] = sb_w[7];
+        } else if (ta == 1) {
+#pragma unroll
+          for (int k = 0; k < 5; ++k) sb_w[k] = sb_w[5];
+        } else if (ta == 2) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) sb_w[k] = sb_w[3];
+        }
+#pragma unroll 1
+        for (int t = ta; t < tb; t += 12) {
+          BVG_FBLOCK(xb, xa, sb_w, sa_w, t, true);
+          BVG_FBLOCK(xa, xb, sa_w, sb_w, t + 6, true);  // past tb: computed, not stored (keeps the windows in step)
+        }
+#undef BVG_FBLOCK
+      }
+    }
+    // generic-proxy writes -> visible to the tensor core (async proxy), then one arrive per warp and slice
+    ptx::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      int s = sa;
+      for (int cb = 0; cb < p.n_cb; ++cb) {
+        ptx::mbar_arrive(a_full(s));
+        if (++s == p.a_stages) s = 0;
+      }
+    }
+    for (int cb = 0; cb < p.n_cb; ++cb)
+      if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+  }
+}
+
 // Epilogue specialisation (compile-time, so the per-element code is a handful of instructions):
 //   OUT  : output format (BVG_F32 | BVG_BF16 | BVG_SPLIT)
 //   SBF  : residual / running-sum tensors are bf16 (else fp32)
 //   RES  : a residual is added            ACC : a running sum is added (and maybe divided)
 //   GEN  : generic fallback -- every choice read from the descriptor at run time, ragged N allowed
-template <int OUT, bool SBF, bool RES, bool ACC, bool GEN>
-__global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_constant__ UmmaParams p) {
+template <int OUT, bool SBF, bool RES, bool ACC, bool GEN, bool FUSED = false>
+__global__ void __launch_bounds__(FUSED ? UM_THREADS_FUSED : UM_THREADS, 1) conv_umma_kernel(const __grid_constant__ UmmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve-up: [A stages][B stages][epilogue staging][barriers][tmem ptr]; base rounded up to 1024 B
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -274,16 +463,16 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&p.tm_x[0]);
+    if (!FUSED) ptx::prefetch_tmap(&p.tm_x[0]);
     ptx::prefetch_tmap(&p.tm_w[0]);
     if (p.planes == 2) {
-      ptx::prefetch_tmap(&p.tm_x[1]);
+      if (!FUSED) ptx::prefetch_tmap(&p.tm_x[1]);
       if (!p.stacked) ptx::prefetch_tmap(&p.tm_w[1]);
     }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.a_stages; ++s) {
-      ptx::mbar_init(a_full(s), 1);
+      ptx::mbar_init(a_full(s), FUSED ? UM_AMP_WARPS : 1);  // fused: one arrive per producer warp
       ptx::mbar_init(a_empty(s), 1);
     }
     for (int s = 0; s < p.b_stages; ++s) {
@@ -325,16 +514,19 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
         const int row0 = t0 + p.min_shift[nt];
         for (int cb = 0; cb < p.n_cb; ++cb) {
           // A super-tile: rows [row0, row0 + a_boxes * a_box_rows) x 64 channels, every plane
-          ptx::mbar_wait(a_empty(sa), pa ^ 1, p.err_flag, 1);
-          if (ptx::elect_one()) {
-            ptx::mbar_expect_tx(a_full(sa), (uint32_t)p.a_stage_bytes);
-            for (int pl = 0; pl < planes; ++pl)
-              for (int bx = 0; bx < p.a_boxes; ++bx)
-                ptx::tma_load_3d(a_base + sa * p.a_stage_bytes + pl * p.a_plane_bytes + bx * box_bytes, &p.tm_x[pl], a_full(sa), cb * UM_KB,
-                                 row0 + bx * p.a_box_rows, b);
+          // (fused mode: written by the Activation1d producer warps instead)
+          if constexpr (!FUSED) {
+            ptx::mbar_wait(a_empty(sa), pa ^ 1, p.err_flag, 1);
+            if (ptx::elect_one()) {
+              ptx::mbar_expect_tx(a_full(sa), (uint32_t)p.a_stage_bytes);
+              for (int pl = 0; pl < planes; ++pl)
+                for (int bx = 0; bx < p.a_boxes; ++bx)
+                  ptx::tma_load_3d(a_base + sa * p.a_stage_bytes + pl * p.a_plane_bytes + bx * box_bytes, &p.tm_x[pl], a_full(sa), cb * UM_KB,
+                                   row0 + bx * p.a_box_rows, b);
+            }
+            __syncwarp();
+            if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
           }
-          __syncwarp();
-          if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
           // weights: one box of tap_group consecutive taps per (group, plane); rows past the last
           // tap of this N tile belong to the next tile (or are zero-filled past the end) and are unused
           const int w_planes = p.stacked ? 1 : planes;   // stacked: hi and lo rows arrive in one box
@@ -431,7 +623,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
         if (++as == p.t_stages) { as = 0; ap ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + UM_EPI_WARPS) {
     // ================================ epilogue ====================================
     // Warp e owns TMEM lane quarter q = e % 4 (rows 32q..32q+31 of every M block) and every second
     // (M block, 16-column chunk) work item.  Each chunk goes TMEM -> registers (thread = row) ->
@@ -608,6 +800,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const __grid_c
     }
   }
 
+  if constexpr (FUSED) {
+    if (warp >= 4 + UM_EPI_WARPS) fused_amp_producer(p, a_base, bar_base);
+  }
+
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -696,17 +892,29 @@ static int plan_smem(int mb, int a_stages, int max_span, int planes, int n_tile,
 int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out) {
   const bvg_conv_weights* w = d->w;
   BVG_REQUIRE(w->backend == BVG_UMMA, "conv_umma: weights were packed for another backend");
-  BVG_REQUIRE(d->x.dtype == BVG_BF16 || d->x.dtype == BVG_SPLIT, "conv_umma: input must be BF16 or SPLIT");
-  const int planes = d->x.dtype == BVG_SPLIT ? 2 : 1;
-  BVG_REQUIRE(planes == 1 || (w->split && (w->split == 2 || w->d_w_lo) && d->x.d_lo), "conv_umma: SPLIT input needs split-packed weights and a lo plane");
+  // fused Activation1d producer: the operand is computed in the kernel from pre_amp->x (fp32); it has the format
+  // the weights were packed for (SPLIT planes for split weights, else BF16)
+  const bvg_amp_desc* fa = d->pre_amp;
+  const bool fused = fa != nullptr;
+  if (fused) {
+    BVG_REQUIRE(fa->x.dtype == BVG_F32 && fa->x.d_ptr && fa->d_a && fa->d_invb, "conv_umma: the fused Activation1d needs an fp32 input and its parameters");
+    BVG_REQUIRE(fa->B == d->B && fa->L == d->L && fa->C == w->cin, "conv_umma: fused Activation1d shape [%d, %d, %d] does not match the convolution [%d, %d, %d]",
+                fa->B, fa->L, fa->C, d->B, d->L, w->cin);
+    BVG_REQUIRE(w->cin % 8 == 0 && w->cin <= UM_KB && w->cin >= 8, "conv_umma: the fused Activation1d takes 8 <= Cin <= 64 (one K slice), Cin %% 8 == 0");
+    BVG_REQUIRE(((uintptr_t)fa->x.d_ptr & 7) == 0, "conv_umma: fused Activation1d input must be 8-byte aligned");
+  } else {
+    BVG_REQUIRE(d->x.dtype == BVG_BF16 || d->x.dtype == BVG_SPLIT, "conv_umma: input must be BF16 or SPLIT");
+  }
+  const int planes = fused ? (w->split ? 2 : 1) : (d->x.dtype == BVG_SPLIT ? 2 : 1);
+  BVG_REQUIRE(planes == 1 || (w->split && (w->split == 2 || w->d_w_lo) && (fused || d->x.d_lo)), "conv_umma: SPLIT input needs split-packed weights and a lo plane");
   const bool stacked = planes == 2 && w->split == 2;
   BVG_REQUIRE(!stacked || 2 * w->n_tile <= 256, "conv_umma: stacked weights need n_tile <= 128");
-  BVG_REQUIRE(d->x.d_ptr && w->d_w, "conv_umma: null pointer");
+  BVG_REQUIRE((fused || d->x.d_ptr) && w->d_w, "conv_umma: null pointer");
   BVG_REQUIRE(d->B > 0 && d->L > 0, "conv_umma: bad shape");
   BVG_REQUIRE(w->n_tile % 16 == 0 && w->n_tile >= 16 && w->n_tile <= 256, "conv_umma: bad n_tile %d", w->n_tile);
   BVG_REQUIRE(w->n_tiles <= BVG_MAX_NTILES, "conv_umma: too many N tiles");
   BVG_REQUIRE(w->x_pitch % 8 == 0, "conv_umma: channel pitch %d must be a multiple of 8 (16-byte TMA strides)", w->x_pitch);
-  BVG_REQUIRE(((uintptr_t)d->x.d_ptr & 15) == 0 && ((uintptr_t)w->d_w & 15) == 0, "conv_umma: operands must be 16-byte aligned");
+  BVG_REQUIRE((fused || ((uintptr_t)d->x.d_ptr & 15) == 0) && ((uintptr_t)w->d_w & 15) == 0, "conv_umma: operands must be 16-byte aligned");
 
   UmmaParams& p = out->p;
   memset(&p, 0, sizeof(p));
@@ -780,6 +988,10 @@ int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out) {
       break;
     }
   }
+  if (fused) {  // the producer of tile i+1 runs under the MMAs of tile i: one spare stage when it fits
+    int br, nb, tg;
+    if (plan_smem(mb, 3, max_span, planes, w_rows, max_taps, &br, &nb, &tg) >= 3) a_stages = 3;
+  }
   if (umma_a_stages >= 2 && umma_a_stages <= UM_MAX_A_STAGES) a_stages = umma_a_stages;
   p.a_stages = a_stages;
   const int bs = plan_smem(mb, a_stages, max_span, planes, w_rows, max_taps, &p.a_box_rows, &p.a_boxes, &p.tap_group);
@@ -795,12 +1007,24 @@ int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out) {
   out->smem = smem;
 
   // tensor maps
+  if (fused) {
+    p.f_x = reinterpret_cast<const float*>(fa->x.d_ptr);
+    p.f_a = fa->d_a;
+    p.f_invb = fa->d_invb;
+    for (int k = 0; k < 12; ++k) {
+      p.f_gu[k] = 2.0f * fa->taps_up[k];
+      p.f_fd[k] = fa->taps_down[k];
+    }
+    p.f_C = fa->C;
+    p.f_need = p.tile_rows + max_span;
+    p.f_fast_sin = fa->fast_sin;
+  }
   for (int pl = 0; pl < planes; ++pl) {
     void* xb = pl == 0 ? d->x.d_ptr : d->x.d_lo;
     cuuint64_t dims[3] = {(cuuint64_t)w->x_pitch, (cuuint64_t)d->L, (cuuint64_t)d->B};
     cuuint64_t strides[2] = {(cuuint64_t)w->x_pitch * 2, (cuuint64_t)w->x_pitch * 2 * (cuuint64_t)d->L};
     cuuint32_t box[3] = {(cuuint32_t)UM_KB, (cuuint32_t)p.a_box_rows, 1};
-    rc = encode_bf16_map(&p.tm_x[pl], xb, 3, dims, strides, box, "activation");
+    rc = fused ? BVG_OK : encode_bf16_map(&p.tm_x[pl], xb, 3, dims, strides, box, "activation");
     if (rc != BVG_OK) return rc;
     void* wb = pl == 0 ? w->d_w : w->d_w_lo;
     if (stacked && pl == 1) continue;  // both weight planes live in d_w
@@ -826,6 +1050,15 @@ static UmmaKernel select_kernel(const UmmaParams& p) {
   const bool sbf = (res && e.res_dtype == BVG_BF16) || (acc && e.acc_dtype == BVG_BF16);
   const bool mixed = (res && acc && e.res_dtype != e.acc_dtype);
   const bool plain = p.vec_ok && !mixed && (acc || !e.use_div) && (!acc || res);
+  if (p.f_x) {  // fused Activation1d producer: the epilogues the fp32 path's resblock convolutions use, else the generic one
+    if (plain && !sbf) {
+      if (e.out_dtype == BVG_F32 && !res) return conv_umma_kernel<BVG_F32, false, false, false, false, true>;
+      if (e.out_dtype == BVG_F32 && res && !acc) return conv_umma_kernel<BVG_F32, false, true, false, false, true>;
+      if (e.out_dtype == BVG_F32 && res && acc) return conv_umma_kernel<BVG_F32, false, true, true, false, true>;
+      if (e.out_dtype == BVG_SPLIT && res && acc) return conv_umma_kernel<BVG_SPLIT, false, true, true, false, true>;
+    }
+    return conv_umma_kernel<BVG_F32, false, false, false, true, true>;
+  }
   if (plain) {
     if (!sbf) {
       if (e.out_dtype == BVG_F32 && !res) return conv_umma_kernel<BVG_F32, false, false, false, false>;
@@ -845,15 +1078,15 @@ int conv_umma_launch(const UmmaLaunch* l, cudaStream_t st) {
   if (l->grid <= 0) return BVG_OK;
   UmmaKernel k = select_kernel(l->p);
   // opt in to > 48 KB of dynamic shared memory once per specialisation (cheap, idempotent)
-  static UmmaKernel configured[16];
+  static UmmaKernel configured[32];
   static int n_configured = 0;
   bool seen = false;
   for (int i = 0; i < n_configured; ++i) seen = seen || configured[i] == k;
   if (!seen) {
     BVG_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_LIMIT));
-    if (n_configured < 16) configured[n_configured++] = k;
+    if (n_configured < 32) configured[n_configured++] = k;
   }
-  k<<<l->grid, UM_THREADS, l->smem, st>>>(l->p);
+  k<<<l->grid, l->p.f_x ? UM_THREADS_FUSED : UM_THREADS, l->smem, st>>>(l->p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "conv_umma_kernel launch");
   return BVG_OK;

@@ -77,11 +77,14 @@ def pack_conv(v, g, bias, *, transposed=False, dilation=1, stride=1, padding=0, 
     return pc
 
 
-def conv(x, pc: _PackedConv, *, x_dtype=None, out_dtype=L.F32, res=None, res_dtype=L.F32, acc=None, acc_dtype=L.F32, div=1.0):
+def conv(x, pc: _PackedConv, *, x_dtype=None, out_dtype=L.F32, res=None, res_dtype=L.F32, acc=None, acc_dtype=L.F32, div=1.0, pre_amp=None):
     """Tap-GEMM convolution of ``x [B, L, x_pitch]`` with packed weights; returns ``[B, L, n_total]``
-    (for a transposed conv reshape to ``[B, L*u, Cout]``)."""
+    (for a transposed conv reshape to ``[B, L*u, Cout]``).  ``pre_amp = (a, invb, taps_up, taps_down, fast_sin)``
+    fuses that Activation1d in front: ``x`` is then its fp32 input (``bvg_conv_desc.pre_amp``)."""
     B, Ln, Cx = x.shape
     assert Cx == pc.x_pitch, f"x has {Cx} channels per row, packed weights expect pitch {pc.x_pitch}"
+    if pre_amp is not None:
+        x_dtype = L.F32
     if x_dtype is None:
         x_dtype = L.F32 if pc.desc.backend == L.SIMT else (L.SPLIT if pc.desc.split else L.BF16)
     xb = to_buf(x, x_dtype)
@@ -95,6 +98,17 @@ def conv(x, pc: _PackedConv, *, x_dtype=None, out_dtype=L.F32, res=None, res_dty
     d.acc_in = ab.tensor() if ab is not None else _NULL
     d.div, d.B, d.L = float(div), B, Ln
     d.w = C.pointer(pc.desc)
+    if pre_amp is not None:
+        a, invb, taps_up, taps_down, fast_sin = pre_amp
+        a = a.contiguous().float()
+        invb = invb.contiguous().float()
+        ad = L.AmpDesc()
+        ad.x = xb.tensor()
+        ad.d_a, ad.d_invb = a.data_ptr(), invb.data_ptr()
+        ad.taps_up = (C.c_float * 12)(*[float(t) for t in taps_up])
+        ad.taps_down = (C.c_float * 12)(*[float(t) for t in taps_down])
+        ad.B, ad.L, ad.C, ad.fast_sin = B, Ln, Cx, int(fast_sin)
+        d.pre_amp = C.cast(C.pointer(ad), C.c_void_p)
     with torch.cuda.device(x.device):
         L.check(L.lib().bvg_conv_fwd(C.byref(d), _stream(x.device)), "conv_fwd")
     return from_buf(ob, (B, Ln, n))

@@ -382,6 +382,58 @@ def test_conv_umma_time_fold(ops, case, split):
         assert np.abs(yf - yu).max() < 2e-3  # same bf16 operands, different accumulation order
 
 
+FUSED_CASES = [
+    # (B, C, L, k, d)
+    (2, 48, 1000, 11, 1),
+    (1, 48, 517, 7, 3),
+    (3, 48, 260, 3, 5),
+    (2, 24, 1500, 11, 5),
+    (1, 24, 333, 3, 1),
+    (1, 64, 700, 7, 1),
+    (1, 8, 200, 7, 5),
+    (2, 40, 129, 11, 3),
+    (1, 48, 5, 7, 1),
+    (1, 24, 1, 3, 1),
+    (4, 48, 4100, 11, 1),
+]
+
+
+@pytest.mark.parametrize("case", FUSED_CASES)
+@pytest.mark.parametrize("epi", ["plain", "res", "res_acc"])
+@pytest.mark.parametrize("fast_sin", [True, False])
+def test_conv_fused_activation1d(ops, case, epi, fast_sin):
+    """bvg_conv_desc.pre_amp: the convolution computes its (hi, lo) operand from the Activation1d's fp32 input inside
+    the kernel.  Same arithmetic as amp_kernel_p2 followed by the unfused convolution, so the results must agree
+    to rounding -- sequence ends (both replicate clamps next to the conv's zero padding), ragged tiles, several
+    tiles per CTA, channel counts that leave pad columns (C = 24, 40, 8), every resblock epilogue."""
+    _ops, L = ops
+    B, Ch, Ln, k, d = case
+    rng = np.random.default_rng(500 + Ch + k + d + Ln)
+    x = (rng.standard_normal((B, Ch, Ln)) * 1.5).astype(np.float32)
+    v = (rng.standard_normal((Ch, Ch, k)) / np.sqrt(Ch * k)).astype(np.float32)
+    g = (np.sqrt((v.astype(np.float64) ** 2).sum(axis=(1, 2), keepdims=True)) * rng.uniform(0.7, 1.4, (Ch, 1, 1))).astype(np.float32)
+    b = (rng.standard_normal(Ch) * 0.1).astype(np.float32)
+    a, invb = snake_params((rng.standard_normal(Ch) * 0.3).astype(np.float32), (rng.standard_normal(Ch) * 0.3).astype(np.float32), True)
+    f = golden_taps()
+    pc = _ops.pack_conv(*(torch.from_numpy(t).to(DEV) for t in (v, g, b)), dilation=d, padding=O.get_padding(k, d), backend=L.UMMA, split=True)
+    res = cl(rng.standard_normal((B, Ch, Ln)).astype(np.float32)) if epi != "plain" else None
+    acc = cl(rng.standard_normal((B, Ch, Ln)).astype(np.float32)) if epi == "res_acc" else None
+    kw = dict(res=res, acc=acc, div=3.0 if epi == "res_acc" else 1.0)
+    xl = cl(x)
+    L.set_tuning("amp_mma", 0)
+    try:
+        z = _ops.activation1d(xl, a, invb, f, f, in_dtype=L.F32, out_dtype=L.SPLIT, fast_sin=fast_sin)
+    finally:
+        L.set_tuning("amp_mma", 1)
+    y_ref = _ops.conv(z, pc, **kw)
+    y_fused = _ops.conv(xl, pc, pre_amp=(a, invb, f, f, fast_sin), **kw)
+    assert torch.isfinite(y_fused).all()
+    # (the unfused reference goes through a float32 copy of the (hi, lo) planes, whose sum can round away the last
+    # bits of a tiny lo term: agreement to fp32 rounding instead of bit equality)
+    err = float((y_fused - y_ref).abs().max())
+    assert err <= 1e-5 * max(1.0, float(y_ref.abs().max())), err
+
+
 def test_conv_umma_large_rows(ops):
     """Many tiles per CTA (pipeline wrap-around of every barrier ring) and ragged last tiles."""
     _umma_conv_check(ops, 4, 48, 20011, 7, 3, split=False, mb=0)
