@@ -258,6 +258,11 @@ class Generator(nn.Module):
         self.max_cached_programs = 6
         # narrow resblock convolutions read four rows as one (see _time_fold); set False + _invalidate() to compare
         self.time_fold = True
+        # Activation1d fused into the following narrow convolution (bvg_conv_desc.pre_amp, see _fuse_amp).  Off: measured
+        # on B200 (gpurun_out/ab_fuse2.txt) a fused C = 48 layer takes 0.73-0.80 ms against 0.18 + 0.16..0.26 ms for the
+        # pair -- the convolution CTA has room for 8 producer warps (one CTA per SM: 512 TMEM columns, ~200 KB of shared
+        # memory) where the stand-alone kernel keeps 24 warps per SM busy and is FMA-pipe bound even so.
+        self.fuse_amp = False
         self.use_cuda_graph = False
         # Two half-batches on two streams, launched op by op in alternation: the tensor-core convolutions of
         # one half (one persistent CTA per SM, ~6 % of the issue slots) share the SMs with the FFMA-bound
@@ -393,6 +398,16 @@ class Generator(nn.Module):
             up *= int(r)
         return fold if up % fold == 0 else 1
 
+    def _fuse_amp(self, cname: str, x_in) -> bool:
+        """Whether the Activation1d in front of convolution ``cname`` runs inside the convolution kernel
+        (``bvg_conv_desc.pre_amp``): fp32 path (fp32 residual stream, split operands), one K slice (Cin <= 64), layer
+        not time-folded."""
+        if not self.fuse_amp or self.precision != "fp32":
+            return False
+        pc = self._packed["conv"][cname]
+        m = self.get_submodule(cname)
+        return pc.fold == 1 and pc.desc.backend == L.UMMA and m.cin % 8 == 0 and 8 <= m.cin <= 64 and x_in.dtype == L.F32
+
     def _umma_ok(self, m: _WNConv) -> bool:
         if m is self.conv_pre:
             return m.cout % 8 == 0
@@ -413,19 +428,38 @@ class Generator(nn.Module):
             fast_sin = 0
         pk = self._packed
         cfg = self.cfg
-        ops, keep = [], []
+        ops, keep, descs = [], [], []
 
         labels = []
         esz = {L.F32: 4, L.BF16: 2, L.SPLIT: 4}
 
-        def conv_op(name, x, out, B_, L_, res=None, acc=None, div=1.0):
+        def amp_desc(name, x, B_, L_, C_):
+            a, invb, up, down = pk["act"][name]
+            d = L.AmpDesc()
+            d.x = x.tensor()
+            d.d_a, d.d_invb = a.data_ptr(), invb.data_ptr()
+            d.taps_up = (C.c_float * 12)(*up)
+            d.taps_down = (C.c_float * 12)(*down)
+            d.B, d.L, d.C, d.fast_sin = B_, L_, C_, fast_sin
+            return d
+
+        def conv_op(name, x, out, B_, L_, res=None, acc=None, div=1.0, pre_amp=None):
+            # pre_amp = (activation name, its input buffer): the Activation1d runs inside the convolution kernel
             m = self.get_submodule(name)
             flops = 2.0 * m.cin * m.cout * m.ksize * B_ * L_
-            labels.append((f"{name} {m.cin}->{m.cout} k{m.ksize} d{m.dilation} u{m.stride} L{L_}", "conv", flops))
+            tag = f" +{pre_amp[0].split('.', 2)[-1]}" if pre_amp is not None else ""
+            labels.append((f"{name} {m.cin}->{m.cout} k{m.ksize} d{m.dilation} u{m.stride} L{L_}{tag}", "conv", flops))
             op = L.Op()
             op.kind = L.OP_CONV
             d = op.u.conv
-            d.x, d.out = x.tensor(), out.tensor()
+            if pre_amp is not None:
+                ad = amp_desc(pre_amp[0], pre_amp[1], B_, L_, m.cin)
+                descs.append(ad)
+                d.pre_amp = C.cast(C.pointer(ad), C.c_void_p)
+                d.x = _NULL
+            else:
+                d.x = x.tensor()
+            d.out = out.tensor()
             d.res = res.tensor() if res is not None else _NULL
             d.acc_in = acc.tensor() if acc is not None else _NULL
             fold = pk["conv"][name].fold
@@ -433,6 +467,14 @@ class Generator(nn.Module):
             d.div, d.B, d.L = float(div), B_, L_ // fold
             d.w = C.pointer(pk["conv"][name].desc)
             ops.append(op)
+
+        def amp_conv(aname, x, cname, out, B_, L_, C_, **epi):
+            """Activation1d -> convolution: one kernel when the layer qualifies (_fuse_amp), else the pair through t_op."""
+            if self._fuse_amp(cname, x):
+                conv_op(cname, None, out, B_, L_, pre_amp=(aname, x), **epi)
+            else:
+                amp_op(aname, x, t_op, B_, L_, C_)
+                conv_op(cname, t_op, out, B_, L_, **epi)
 
         def amp_op(name, x, y, B_, L_, C_):
             labels.append((f"{name} C{C_} L{L_}", "amp", float(B_) * L_ * C_ * (esz[x.dtype] + esz[y.dtype])))
@@ -501,23 +543,22 @@ class Generator(nn.Module):
                 for l in range(nl):
                     final = l == nl - 1
                     if block1:
-                        amp_op(f"{rb}.activations.{2 * l}", xj, t_op, B, ln, ch)
-                        conv_op(f"{rb}.convs1.{l}", t_op, t_mid, B, ln)
-                        amp_op(f"{rb}.activations.{2 * l + 1}", t_mid, t_op, B, ln, ch)
+                        amp_conv(f"{rb}.activations.{2 * l}", xj, f"{rb}.convs1.{l}", t_mid, B, ln, ch)
+                        aname, ain = f"{rb}.activations.{2 * l + 1}", t_mid
                         cname = f"{rb}.convs2.{l}"
                     else:
-                        amp_op(f"{rb}.activations.{l}", xj, t_op, B, ln, ch)
+                        aname, ain = f"{rb}.activations.{l}", xj
                         cname = f"{rb}.convs.{l}"
                     if not final:
-                        conv_op(cname, t_op, xa, B, ln, res=xj)
+                        amp_conv(aname, ain, cname, xa, B, ln, ch, res=xj)
                         xj = xa
                     elif j == 0 and nk > 1:
-                        conv_op(cname, t_op, xs, B, ln, res=xj)
+                        amp_conv(aname, ain, cname, xs, B, ln, ch, res=xj)
                     elif j < nk - 1:
-                        conv_op(cname, t_op, xs, B, ln, res=xj, acc=xs)
+                        amp_conv(aname, ain, cname, xs, B, ln, ch, res=xj, acc=xs)
                     else:
                         # last resblock: (xs + this) / num_kernels, stored in the next consumer's format
-                        conv_op(cname, t_op, stage_out, B, ln, res=xj, acc=(xs if nk > 1 else None), div=float(nk))
+                        amp_conv(aname, ain, cname, stage_out, B, ln, ch, res=xj, acc=(xs if nk > 1 else None), div=float(nk))
             cur, nxt = nxt, cur
             l_in = ln
 
@@ -534,6 +575,7 @@ class Generator(nn.Module):
         labels.append(("conv_post+tanh", "post", 0.0))
         prog = _Program(ops, keep, mel_in, out, len(ops))
         prog.labels = labels
+        prog.descs = descs  # ctypes descriptors the ops point to
         return prog
 
     def _program(self, B: int, T: int, slot: int = -1) -> _Program:

@@ -292,3 +292,29 @@ def test_time_folded_layers_match_unfolded(repo_model, precision):
     else:
         snr = 10 * np.log10(float((y_plain.double() ** 2).sum() / ((y_fold - y_plain).double() ** 2).sum()))
         assert snr > 45, snr
+
+
+def test_fused_activation_layers_match_unfused(repo_model):
+    """Generator.fuse_amp: the Activation1d in front of every C <= 64 unfolded resblock convolution runs inside the
+    convolution kernel (bvg_conv_desc.pre_amp).  Same arithmetic in the same order as the two-kernel pair."""
+    from svc_inference_pipeline_b200.utils import synth
+
+    m = repo_model
+    mel = torch.from_numpy(synth.synthetic_mel(2, 100, 33, 92)).cuda()
+    y_plain = m(mel).clone()
+    try:
+        m.fuse_amp = True
+        m._invalidate()
+        y_fused = m(mel).clone()
+        fused = [lab for lab, kind, _ in m._program(1, 33, slot=0).labels if "+activations" in lab]
+        m.time_fold = False  # then the C = 24 stage fuses as well
+        m._invalidate()
+        y_fused_all = m(mel).clone()
+        fused_all = [lab for lab, kind, _ in m._program(1, 33, slot=0).labels if "+activations" in lab]
+    finally:
+        m.fuse_amp = False
+        m.time_fold = True
+        m._invalidate()
+    assert len(fused) == 18 and len(fused_all) == 36, (len(fused), len(fused_all))
+    assert float((y_fused - y_plain).abs().max()) < 2e-6
+    assert float((y_fused_all - y_plain).abs().max()) < 2e-6
