@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BVG_ABI_VERSION 1
+#define BVG_ABI_VERSION 2  /* 2: bvg_conv_geom.fold, bvg_conv_desc.pre_amp */
 
 enum bvg_status {
   BVG_OK = 0,
@@ -252,7 +252,7 @@ void bvg_program_destroy(bvg_program* p);
 int bvg_abi_version(void);
 const char* bvg_last_error(void);
 int bvg_device_check(int device); /* BVG_OK iff `device` is compute capability 10.x */
-int bvg_set_tuning(const char* name, int value); /* test / tuning knobs: amp_vec, amp_chunk, amp_mma, amp_mma_tiles, amp_packed, amp_stream, umma_mb, umma_wide_mb2, umma_max_ctas, umma_ntile_cap, umma_tap_group, umma_a_stages, umma_stack */
+int bvg_set_tuning(const char* name, int value); /* test / tuning knobs: amp_vec, amp_chunk, amp_mma, amp_mma_tiles, amp_packed, amp_stream, amp_stream_bf16, amp_ct, umma_mb, umma_wide_mb2, umma_max_ctas, umma_ntile_cap, umma_tap_group, umma_a_stages, umma_stack */
 size_t bvg_sizeof_op(void);       /* ABI self-check for the ctypes mirror */
 size_t bvg_sizeof_conv_weights(void);
 

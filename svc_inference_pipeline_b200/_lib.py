@@ -205,8 +205,8 @@ def lib():
         fn = getattr(L, name)
         fn.argtypes = argtypes
         fn.restype = None if name == "bvg_program_destroy" else C.c_int
-    if L.bvg_abi_version() != 1:
-        raise BvgError(f"ABI mismatch: library reports version {L.bvg_abi_version()}, binding expects 1")
+    if L.bvg_abi_version() != 2:
+        raise BvgError(f"ABI mismatch: library reports version {L.bvg_abi_version()}, binding expects 2")
     if L.bvg_sizeof_op() != C.sizeof(Op) or L.bvg_sizeof_conv_weights() != C.sizeof(ConvWeights):
         raise BvgError(
             f"struct layout mismatch: C sizeof(bvg_op)={L.bvg_sizeof_op()} vs ctypes {C.sizeof(Op)}; "

@@ -117,7 +117,7 @@ def test_capi_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/bvg_b200.h but not exported"
     assert sorted(L.EXPORTS) == names
-    assert lib.bvg_abi_version() == 1
+    assert lib.bvg_abi_version() == 2
     assert lib.bvg_sizeof_op() == C.sizeof(L.Op)
     assert lib.bvg_sizeof_conv_weights() == C.sizeof(L.ConvWeights)
 
