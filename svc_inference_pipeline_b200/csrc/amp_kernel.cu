@@ -241,7 +241,7 @@ __device__ __forceinline__ P2 load_row2(const void* base, long long off) {
 // that ncu counted as address arithmetic and edge selects (profiles/r01_ncu_summary_v7.md -> _v13.md).
 template <bool IN_BF16, int OUT_MODE, bool FAST_SIN, bool STORE, bool INTERIOR, int CT>
 __device__ __forceinline__ void amp_block6_p2(const AmpParams& p, const P2 (&xa)[6], P2 (&xb)[6], const P2 (&sa)[12], P2 (&sb)[12], int tau0,
-                                              long long base, P2 apar, P2 invb) {
+                                              long long base, P2 apar, P2 invb, bool prefetch = false) {
   const int L = p.L;
   const int Cc = CT ? CT : p.C;
   if constexpr (INTERIOR) {
@@ -251,11 +251,14 @@ __device__ __forceinline__ void amp_block6_p2(const AmpParams& p, const P2 (&xa)
     // L1 prefetch of the rows two blocks ahead (12 rows past the ones just requested): holds no registers, and
     // the demand loads two blocks later hit on chip.  ncu before: 5.9 stall cycles per issue on the global loads
     // (long scoreboard) at 24 resident warps; measured in-program +5..17 % (gpurun_out/ab_pf.txt; 6, 18, 24, 36 rows
-    // or an L2-only prefetch are behind).  Past the end of the tensor the prefetch is a dropped hint.
+    // or an L2-only prefetch are behind).  A chunk prefetches up to 12 rows past its own end (the next chunk's rows,
+    // or the next batch item's); `prefetch` is false where that would leave the tensor.
+    if (prefetch) {
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      const char* a = reinterpret_cast<const char*>(p.x) + (row0 + (long long)(12 + j) * Cc) * (IN_BF16 ? 2 : 4);
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+      for (int j = 0; j < 6; ++j) {
+        const char* a = reinterpret_cast<const char*>(p.x) + (row0 + (long long)(12 + j) * Cc) * (IN_BF16 ? 2 : 4);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+      }
     }
   } else {
 #pragma unroll
@@ -350,15 +353,16 @@ __global__ void __launch_bounds__(128, 6) amp_kernel_p2(const __grid_constant__ 
   // a per-block choice inside one loop costs registers.
   if (t0 + TT + 5 <= L - 1) {
     // warm-up block (tau = t0-6 .. t0-1): fills sb = s[2 t0 - 7 .. 2 t0 + 4], no output
-    amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, false, true, CT>(p, xa, xb, sa, sb, t0 - 6, base, apar, invb);
+    const bool pf = b + 1 < p.B || t0 + TT + 17 <= L - 1;  // every prefetched row lies inside the tensor
+    amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, false, true, CT>(p, xa, xb, sa, sb, t0 - 6, base, apar, invb, pf);
     if (t0 == 0) {  // left replicate clamp of the activated signal: s[j < 0] = s[0] (slot 7)
 #pragma unroll
       for (int k = 0; k < 7; ++k) sb[k] = sb[7];
     }
     int t = t0;
     for (int i = 0; i < p.nblk2; ++i) {
-      amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, true, true, CT>(p, xb, xa, sb, sa, t, base, apar, invb);
-      amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, true, true, CT>(p, xa, xb, sa, sb, t + 6, base, apar, invb);
+      amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, true, true, CT>(p, xb, xa, sb, sa, t, base, apar, invb, pf);
+      amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, true, true, CT>(p, xa, xb, sa, sb, t + 6, base, apar, invb, pf);
       t += 12;
     }
     return;

@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(32 * NG) amp_mma_kernel(const __grid_constant_
   // upsample (MMA) -> snake -> [EDGE: replicate clamps of the activated signal] -> A fragments
   auto s_block = [&](auto edge_tag, int m, uint32_t addr, SFrag& out) {
     constexpr bool EDGE = decltype(edge_tag)::value;
-    uint32_t xh[4], xl[4];
+    [[maybe_unused]] uint32_t xh[4], xl[4];
     amm::ldmatrix_x4_trans(addr, xh);
     if constexpr (NPL == 2) amm::ldmatrix_x4_trans(addr + PLANE, xl);
     float d[2][4];

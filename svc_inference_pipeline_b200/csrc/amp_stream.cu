@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(32 * RS_WARPS) amp_stream_kernel(const __grid_
   // s-block m from the 16 ring rows starting at walk row `row0` (a multiple of 8)
   auto s_block = [&](auto edge_tag, int m, int row0, SFrag& out) {
     constexpr bool EDGE = decltype(edge_tag)::value;
-    uint32_t xh[4], xl[4];
+    [[maybe_unused]] uint32_t xh[4], xl[4];
     if constexpr (BF16_PATH) {
       amm::ldmatrix_x4_trans(ring_u32 + (uint32_t)(((row0 + frag_row8) & (RS_ROWS - 1)) * RS_PITCH) + frag_off, xh);
     } else {
