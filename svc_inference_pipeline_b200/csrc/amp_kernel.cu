@@ -6,7 +6,7 @@
 //
 // Math (pinned by tests/golden/activation1d.npz):
 //   u[2i]   = sum_m g[2m+1] x[clamp(i+2-m)],  u[2i+1] = sum_m g[2m] x[clamp(i+3-m)],  g = 2*f_up
-//   s[j]    = u[j] + invb * sin^2(a * u[j])
+//   s[j]    = u[j] + invb * sin^2(a * u[j])     (evaluated as u - (invb/2) cos(2 a u) + invb/2, amp_p2.cuh)
 //   z[t]    = sum_k f_down[k] * s[clamp(2t + k - 5, 0, 2L-1)]
 // Two different replicate clamps: on x (1x rate) and on the *activated* s (2x rate).
 //
@@ -28,6 +28,7 @@ struct AmpParams {
   const float* invb;
   float gu[12];  // 2 * upsample taps (the ratio gain of bigvgan.py:282 folded in; exact, power of two)
   float fd[12];  // downsample taps
+  float fsum;    // their sum (fp32, tap 0 .. 11): what a constant comes out of the low-pass as
   int B, L, C;
   int CG;       // channel groups = C / VEC
   int nchunks;  // time chunks per batch item
@@ -103,7 +104,7 @@ __device__ __forceinline__ void store_row(void* y, void* y_lo, long long off, co
 template <bool IN_BF16, int OUT_MODE, int VEC, bool FAST_SIN, bool STORE>
 __device__ __forceinline__ void amp_block6(const AmpParams& p, const float (&xa)[6][VEC], float (&xb)[6][VEC],
                                            const float (&sa)[12][VEC], float (&sb)[12][VEC], int tau0, long long in_base,
-                                           long long out_base, const float (&apar)[VEC], const float (&invb)[VEC]) {
+                                           long long out_base, const float (&apar)[VEC], const float (&invb)[VEC], const float (&zc)[VEC]) {
   const int L = p.L;
   // rows x[tau0+6 .. tau0+11] feed the *next* block; issue them first so they are in flight
   // while this block computes.
@@ -149,7 +150,7 @@ __device__ __forceinline__ void amp_block6(const AmpParams& p, const float (&xa)
     if constexpr (STORE) {
       float z[VEC];
 #pragma unroll
-      for (int c = 0; c < VEC; ++c) z[c] = 0.f;
+      for (int c = 0; c < VEC; ++c) z[c] = zc[c];
 #pragma unroll
       for (int k = 0; k < 12; ++k) {
         const int i = 2 * j + 2 + k;  // slot in (sa ++ sb) of s[2 tau - 5 + k]
@@ -177,12 +178,13 @@ __global__ void __launch_bounds__(128) amp_kernel(const __grid_constant__ AmpPar
   const int L = p.L;
   const long long base = (long long)b * L * p.C + (long long)cg * VEC;
 
-  float apar[VEC], invb[VEC];
+  float apar[VEC], invb[VEC], zc[VEC];  // cosine-form constants (amp_p2.cuh): 2a | a/pi, -invb/2, (invb/2) sum(taps)
 #pragma unroll
   for (int c = 0; c < VEC; ++c) {
-    const float a = __ldg(p.a + cg * VEC + c);
-    apar[c] = FAST_SIN ? a : a * 0.318309886183790672f;
-    invb[c] = __ldg(p.invb + cg * VEC + c);
+    const float ib = __ldg(p.invb + cg * VEC + c);
+    apar[c] = snake_apar2<FAST_SIN>(__ldg(p.a + cg * VEC + c));
+    invb[c] = snake_hbn(ib);
+    zc[c] = snake_zc(ib, p.fsum);
   }
 
   float xa[6][VEC], xb[6][VEC], sa[12][VEC], sb[12][VEC];
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(128) amp_kernel(const __grid_constant__ AmpPar
     load_row<IN_BF16, VEC>(p.x, base + (long long)r * p.C, xa[k]);
   }
   // warm-up block (tau = t0-6 .. t0-1): fills sb = s[2 t0 - 7 .. 2 t0 + 4], no output
-  amp_block6<IN_BF16, OUT_MODE, VEC, FAST_SIN, false>(p, xa, xb, sa, sb, t0 - 6, base, base, apar, invb);
+  amp_block6<IN_BF16, OUT_MODE, VEC, FAST_SIN, false>(p, xa, xb, sa, sb, t0 - 6, base, base, apar, invb, zc);
   if (t0 == 0) {  // left replicate clamp of the activated signal: s[j < 0] = s[0] (slot 7)
 #pragma unroll
     for (int k = 0; k < 7; ++k)
@@ -206,10 +208,10 @@ __global__ void __launch_bounds__(128) amp_kernel(const __grid_constant__ AmpPar
   int t = t0;
   for (int i = 0; i < p.nblk2; ++i) {
     if (t >= L) break;
-    amp_block6<IN_BF16, OUT_MODE, VEC, FAST_SIN, true>(p, xb, xa, sb, sa, t, base, base, apar, invb);
+    amp_block6<IN_BF16, OUT_MODE, VEC, FAST_SIN, true>(p, xb, xa, sb, sa, t, base, base, apar, invb, zc);
     t += 6;
     if (t >= L) break;
-    amp_block6<IN_BF16, OUT_MODE, VEC, FAST_SIN, true>(p, xa, xb, sa, sb, t, base, base, apar, invb);
+    amp_block6<IN_BF16, OUT_MODE, VEC, FAST_SIN, true>(p, xa, xb, sa, sb, t, base, base, apar, invb, zc);
     t += 6;
   }
 }
@@ -241,7 +243,7 @@ __device__ __forceinline__ P2 load_row2(const void* base, long long off) {
 // that ncu counted as address arithmetic and edge selects (profiles/r01_ncu_summary_v7.md -> _v13.md).
 template <bool IN_BF16, int OUT_MODE, bool FAST_SIN, bool STORE, bool INTERIOR, int CT>
 __device__ __forceinline__ void amp_block6_p2(const AmpParams& p, const P2 (&xa)[6], P2 (&xb)[6], const P2 (&sa)[12], P2 (&sb)[12], int tau0,
-                                              long long base, P2 apar, P2 invb, bool prefetch = false) {
+                                              long long base, P2 apar, P2 invb, P2 zc, bool prefetch = false) {
   const int L = p.L;
   const int Cc = CT ? CT : p.C;
   if constexpr (INTERIOR) {
@@ -291,7 +293,7 @@ __device__ __forceinline__ void amp_block6_p2(const AmpParams& p, const P2 (&xa)
     sb[2 * j] = pa;
     sb[2 * j + 1] = pb;
     if constexpr (STORE) {
-      P2 z = 0ull;
+      P2 z = zc;
 #pragma unroll
       for (int k = 0; k < 12; ++k) {
         const int i = 2 * j + 2 + k;  // slot in (sa ++ sb) of s[2 tau - 5 + k]
@@ -336,9 +338,11 @@ __global__ void __launch_bounds__(128, 6) amp_kernel_p2(const __grid_constant__ 
   const int L = p.L;
   const long long base = (long long)b * L * Cc + (long long)cg * 2;
 
-  const float a0 = __ldg(p.a + cg * 2), a1 = __ldg(p.a + cg * 2 + 1);
-  const P2 apar = FAST_SIN ? pk2(a0, a1) : pk2(a0 * 0.318309886183790672f, a1 * 0.318309886183790672f);
-  const P2 invb = pk2(__ldg(p.invb + cg * 2), __ldg(p.invb + cg * 2 + 1));
+  // cosine-form constants (amp_p2.cuh): 2a | a/pi, -invb/2, (invb/2) sum(taps)
+  const float ib0 = __ldg(p.invb + cg * 2), ib1 = __ldg(p.invb + cg * 2 + 1);
+  const P2 apar = pk2(snake_apar2<FAST_SIN>(__ldg(p.a + cg * 2)), snake_apar2<FAST_SIN>(__ldg(p.a + cg * 2 + 1)));
+  const P2 invb = pk2(snake_hbn(ib0), snake_hbn(ib1));
+  const P2 zc = pk2(snake_zc(ib0, p.fsum), snake_zc(ib1, p.fsum));
 
   P2 xa[6], xb[6], sa[12], sb[12];
 #pragma unroll
@@ -354,20 +358,20 @@ __global__ void __launch_bounds__(128, 6) amp_kernel_p2(const __grid_constant__ 
   if (t0 + TT + 5 <= L - 1) {
     // warm-up block (tau = t0-6 .. t0-1): fills sb = s[2 t0 - 7 .. 2 t0 + 4], no output
     const bool pf = b + 1 < p.B || t0 + TT + 17 <= L - 1;  // every prefetched row lies inside the tensor
-    amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, false, true, CT>(p, xa, xb, sa, sb, t0 - 6, base, apar, invb, pf);
+    amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, false, true, CT>(p, xa, xb, sa, sb, t0 - 6, base, apar, invb, zc, pf);
     if (t0 == 0) {  // left replicate clamp of the activated signal: s[j < 0] = s[0] (slot 7)
 #pragma unroll
       for (int k = 0; k < 7; ++k) sb[k] = sb[7];
     }
     int t = t0;
     for (int i = 0; i < p.nblk2; ++i) {
-      amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, true, true, CT>(p, xb, xa, sb, sa, t, base, apar, invb, pf);
-      amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, true, true, CT>(p, xa, xb, sa, sb, t + 6, base, apar, invb, pf);
+      amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, true, true, CT>(p, xb, xa, sb, sa, t, base, apar, invb, zc, pf);
+      amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, true, true, CT>(p, xa, xb, sa, sb, t + 6, base, apar, invb, zc, pf);
       t += 12;
     }
     return;
   }
-  amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, false, false, CT>(p, xa, xb, sa, sb, t0 - 6, base, apar, invb);
+  amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, false, false, CT>(p, xa, xb, sa, sb, t0 - 6, base, apar, invb, zc);
   if (t0 == 0) {
 #pragma unroll
     for (int k = 0; k < 7; ++k) sb[k] = sb[7];
@@ -375,10 +379,10 @@ __global__ void __launch_bounds__(128, 6) amp_kernel_p2(const __grid_constant__ 
   int t = t0;
   for (int i = 0; i < p.nblk2; ++i) {
     if (t >= L) break;
-    amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, true, false, CT>(p, xb, xa, sb, sa, t, base, apar, invb);
+    amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, true, false, CT>(p, xb, xa, sb, sa, t, base, apar, invb, zc);
     t += 6;
     if (t >= L) break;
-    amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, true, false, CT>(p, xa, xb, sa, sb, t, base, apar, invb);
+    amp_block6_p2<IN_BF16, OUT_MODE, FAST_SIN, true, false, CT>(p, xa, xb, sa, sb, t, base, apar, invb, zc);
     t += 6;
   }
 }
@@ -498,6 +502,8 @@ int amp_forward(const bvg_amp_desc* d, cudaStream_t st) {
     p.gu[k] = 2.0f * d->taps_up[k];
     p.fd[k] = d->taps_down[k];
   }
+  p.fsum = 0.f;
+  for (int k = 0; k < 12; ++k) p.fsum += d->taps_down[k];
   p.B = d->B;
   p.L = d->L;
   p.C = d->C;

@@ -6,22 +6,32 @@
 
 namespace bvg {
 
-// sin(a*u): FAST = MUFU on the raw product (phase error ~|a*u| * 1e-7, like the reference's own
-// fp32 rounding of a*u); otherwise reduce exactly to [-pi/2, pi/2] first (sin^2 has period pi),
-// which keeps MUFU.SIN in its most accurate range (abs err 2^-21).  apar = a (FAST) or a/pi.
+// Snake in cosine form.  s = u + invb sin^2(a u) = (u - (invb / 2) cos(2 a u)) + invb / 2: the kernels carry
+// s' = s - invb / 2 through the low-pass and start its accumulator at (invb / 2) * sum(taps) instead of 0 (replicate
+// padding and the FIR both pass a constant through), which saves the squaring: one multiply, one MUFU.COS and one
+// FMA per sample.  ncu: the fp32-path kernel is FMA-pipe bound, this is 4 of its 66 pipe cycles per step.
+//   apar2 = 2 a (FAST: MUFU on the raw product, phase error ~|2 a u| * 1e-7, like the reference's own fp32
+//           rounding of a u) or a / pi (turns of the angle 2 a u, reduced exactly to [-1/2, 1/2] first, which keeps
+//           MUFU.COS in its most accurate range);  hbn = -invb / 2.
 template <bool FAST_SIN>
-__device__ __forceinline__ float snake_one(float u, float apar, float invb) {
-  float s;
+__device__ __forceinline__ float snake_one(float u, float apar2, float hbn) {
+  float c;
   if constexpr (FAST_SIN) {
-    s = __sinf(u * apar);
+    c = __cosf(u * apar2);
   } else {
-    float t = u * apar;               // half-turns
-    float k = (t + 12582912.0f) - 12582912.0f;  // rint for |t| < 2^22
-    float r = t - k;                  // [-0.5, 0.5]
-    s = __sinf(r * 3.14159265358979f);
+    float t = u * apar2;                          // turns
+    float k = (t + 12582912.0f) - 12582912.0f;    // rint for |t| < 2^22
+    float r = t - k;                              // [-0.5, 0.5]
+    c = __cosf(r * 6.28318530717958648f);
   }
-  return fmaf(invb, s * s, u);
+  return fmaf(c, hbn, u);
 }
+
+// per-channel constants of the cosine form from a = exp(alpha) and invb = 1 / (exp(beta) + eps)
+template <bool FAST_SIN>
+__device__ __forceinline__ float snake_apar2(float a) { return FAST_SIN ? 2.0f * a : a * 0.318309886183790672f; }
+__device__ __forceinline__ float snake_hbn(float invb) { return -0.5f * invb; }
+__device__ __forceinline__ float snake_zc(float invb, float tap_sum) { return (0.5f * invb) * tap_sum; }
 
 typedef unsigned long long P2;  // two packed fp32 (channel c in the low half, c+1 in the high half)
 
@@ -47,20 +57,19 @@ __device__ __forceinline__ P2 add2(P2 a, P2 b) {
   return d;
 }
 
-// same operation order as snake_one, two channels at a time (apar = a or a/pi, see snake_one)
+// same operation order as snake_one, two channels at a time
 template <bool FAST_SIN>
-__device__ __forceinline__ P2 snake_two(P2 u, P2 apar, P2 invb) {
-  P2 arg = mul2(u, apar);
+__device__ __forceinline__ P2 snake_two(P2 u, P2 apar2, P2 hbn) {
+  P2 arg = mul2(u, apar2);
   if constexpr (!FAST_SIN) {
     const P2 magic = pk2(12582912.0f, 12582912.0f), nmagic = pk2(-12582912.0f, -12582912.0f);
     const P2 k = add2(add2(arg, magic), nmagic);              // rint for |t| < 2^22
-    arg = fma2(k, pk2(-1.0f, -1.0f), arg);                     // [-0.5, 0.5] half-turns (exact)
-    arg = mul2(arg, pk2(3.14159265358979f, 3.14159265358979f));
+    arg = fma2(k, pk2(-1.0f, -1.0f), arg);                     // [-0.5, 0.5] turns (exact)
+    arg = mul2(arg, pk2(6.28318530717958648f, 6.28318530717958648f));
   }
   float a0, a1;
   upk2(arg, a0, a1);
-  const P2 s = pk2(__sinf(a0), __sinf(a1));
-  return fma2(invb, mul2(s, s), u);
+  return fma2(pk2(__cosf(a0), __cosf(a1)), hbn, u);
 }
 
 }  // namespace bvg

@@ -79,7 +79,7 @@ struct UmmaParams {
   const float* f_x;     // [B, L, f_C] fp32, channels-last
   const float* f_a;
   const float* f_invb;
-  float f_gu[12], f_fd[12];
+  float f_gu[12], f_fd[12], f_fsum;
   int f_C;
   int f_need;           // rows of an A stage the MMAs read: tile_rows + max shift - min shift
   int f_fast_sin;
@@ -271,7 +271,7 @@ __device__ __forceinline__ int issue_stage(const UmmaParams& p, const int* __res
 template <bool FAST_SIN>
 __device__ __forceinline__ void fused_block6(const UmmaParams& p, const P2 (&xa)[6], P2 (&xb)[6], const P2 (&sa)[12], P2 (&sb)[12], int tau0,
                                              const float* __restrict__ xcol, int t_lo, int t_hi, int trow0, uint32_t pair_base, P2 apar, P2 invb,
-                                             bool store) {
+                                             P2 zc, bool store) {
   const int L = p.L, C = p.f_C;
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
@@ -300,7 +300,7 @@ __device__ __forceinline__ void fused_block6(const UmmaParams& p, const P2 (&xa)
     sb[2 * j] = pa;
     sb[2 * j + 1] = pb;
     if (store) {
-      P2 z = 0ull;
+      P2 z = zc;
 #pragma unroll
       for (int k = 0; k < 12; ++k) {
         const int i = 2 * j + 2 + k;
@@ -340,9 +340,12 @@ __device__ __forceinline__ void fused_amp_producer(const UmmaParams& p, uint32_t
   const int cb_mine = c >> 6;
   const uint32_t col_bytes = (uint32_t)((c & 63) * 2);
   const float a0 = __ldg(p.f_a + c), a1 = __ldg(p.f_a + c + 1);
+  const float ib0 = __ldg(p.f_invb + c), ib1 = __ldg(p.f_invb + c + 1);
   const bool fast = p.f_fast_sin != 0;
-  const P2 apar = fast ? pk2(a0, a1) : pk2(a0 * 0.318309886183790672f, a1 * 0.318309886183790672f);
-  const P2 invb = pk2(__ldg(p.f_invb + c), __ldg(p.f_invb + c + 1));
+  // cosine-form constants (amp_p2.cuh): 2a | a/pi, -invb/2, (invb/2) sum(taps)
+  const P2 apar = fast ? pk2(snake_apar2<true>(a0), snake_apar2<true>(a1)) : pk2(snake_apar2<false>(a0), snake_apar2<false>(a1));
+  const P2 invb = pk2(snake_hbn(ib0), snake_hbn(ib1));
+  const P2 zc = pk2(snake_zc(ib0, p.f_fsum), snake_zc(ib1, p.f_fsum));
   auto a_full = [&](int s) { return bar_base + 8u * s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (UM_MAX_A_STAGES + s); };
 
@@ -397,8 +400,8 @@ __device__ __forceinline__ void fused_amp_producer(const UmmaParams& p, uint32_t
           xa[k] = pk2(t.x, t.y);
         }
 #define BVG_FBLOCK(XA, XB, SA, SB, TAU, STORE)                                                                  \
-  if (fast) fused_block6<true>(p, XA, XB, SA, SB, TAU, xcol, ta, tb, trow0, pair_base, apar, invb, STORE);     \
-  else fused_block6<false>(p, XA, XB, SA, SB, TAU, xcol, ta, tb, trow0, pair_base, apar, invb, STORE)
+  if (fast) fused_block6<true>(p, XA, XB, SA, SB, TAU, xcol, ta, tb, trow0, pair_base, apar, invb, zc, STORE); \
+  else fused_block6<false>(p, XA, XB, SA, SB, TAU, xcol, ta, tb, trow0, pair_base, apar, invb, zc, STORE)
         BVG_FBLOCK(xa, xb, sa_w, sb_w, ta - 6, false);  // warm-up: fills the s window, no output
         // left replicate clamp of the activated signal: s[j < 0] = s[0].  The window holds s[2 ta - 7 + k]; a run may
         // start at any row here (amp_kernel_p2's chunks start at 0 or far from it), so s[0] sits in slot 7 - 2 ta
@@ -1015,6 +1018,8 @@ int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out) {
       p.f_gu[k] = 2.0f * fa->taps_up[k];
       p.f_fd[k] = fa->taps_down[k];
     }
+    p.f_fsum = 0.f;
+    for (int k = 0; k < 12; ++k) p.f_fsum += fa->taps_down[k];
     p.f_C = fa->C;
     p.f_need = p.tile_rows + max_span;
     p.f_fast_sin = fa->fast_sin;

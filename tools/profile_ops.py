@@ -15,7 +15,7 @@ ap.add_argument("--frames", type=int, default=938)
 ap.add_argument("--out", default=None)
 ap.add_argument("--tune", action="append", default=[], help="name=value tuning knob (bvg_set_tuning)")
 ap.add_argument("--no-fold", action="store_true", help="narrow convolutions without time folding")
-ap.add_argument("--no-fuse", action="store_true", help="no Activation1d fused into the narrow convolutions")
+ap.add_argument("--fuse", action="store_true", help="Activation1d fused into the narrow convolutions (Generator.fuse_amp, off by default)")
 a = ap.parse_args()
 from svc_inference_pipeline_b200 import _lib as _L
 for kv in a.tune:
@@ -24,7 +24,7 @@ for kv in a.tune:
 cfg = load_config(os.path.join(ROOT, "svc_inference_pipeline_b200", "config", "config.json"))
 m = Generator(cfg.vocoder, precision=a.precision)
 m.time_fold = not a.no_fold
-m.fuse_amp = not a.no_fuse
+m.fuse_amp = a.fuse
 m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.synthetic_state_dict({k: cfg.vocoder[k] for k in cfg.vocoder.keys()}, 0).items()})
 m = m.cuda().eval()
 mel = torch.from_numpy(synth.synthetic_mel(a.batch, 100, a.frames, 1235)).cuda()
