@@ -151,6 +151,55 @@ def test_conv_geometry_tables():
     assert b"BVG_MAX_TAPS" in lib.bvg_last_error()
 
 
+def test_conv_geometry_time_fold():
+    """bvg_conv_geom.fold (host part): the folded layer's sizes and tap table, and -- in numpy, with the oracle's
+    conv1d -- that the block-Toeplitz arrangement pack.cu::folded_weight implements is the same convolution."""
+    from oracle import bigvgan_oracle as O
+    from svc_inference_pipeline_b200 import _lib as L
+
+    lib = L.lib()
+
+    def geom(*a):
+        g, w = L.ConvGeom(*a), L.ConvWeights()
+        rc = lib.bvg_conv_geometry(C.byref(g), C.byref(w))
+        return rc, w
+
+    rc, w = geom(0, 24, 24, 11, 1, 1, 5, L.UMMA, 1, 0, 4)
+    assert rc == 0 and (w.cin, w.n_total, w.x_pitch, w.cin_pad, w.n_tiles, w.n_taps[0]) == (96, 96, 96, 128, 1, 5)
+    assert list(w.shift[0])[:5] == [-2, -1, 0, 1, 2]
+    rc, w = geom(0, 24, 24, 11, 5, 1, 25, L.UMMA, 0, 0, 4)
+    assert rc == 0 and w.n_taps[0] == 15 and list(w.shift[0])[:15] == list(range(-7, 8))
+    rc, w = geom(0, 24, 24, 3, 1, 1, 1, L.UMMA, 0, 0, 4)
+    assert rc == 0 and list(w.shift[0])[:3] == [-1, 0, 1]
+    assert geom(1, 48, 24, 4, 1, 2, 1, L.UMMA, 0, 0, 2)[0] != 0   # transposed convs do not fold
+    assert geom(0, 24, 24, 11, 1, 1, 5, L.SIMT, 0, 0, 4)[0] != 0  # nor does the SIMT backend
+    rc, w1 = geom(0, 24, 24, 11, 1, 1, 5, L.UMMA, 0, 0, 1)
+    rc, w0 = geom(0, 24, 24, 11, 1, 1, 5, L.UMMA, 0, 0, 0)
+    assert (w1.cin, w1.n_total, w1.n_taps[0]) == (w0.cin, w0.n_total, w0.n_taps[0]) == (24, 24, 11)
+
+    rng = np.random.default_rng(5)
+    for (ch, k, d, P, Ln) in [(6, 11, 1, 4, 40), (4, 7, 3, 4, 24), (4, 3, 5, 2, 18), (2, 11, 5, 4, 64)]:
+        pad = O.get_padding(k, d)
+        wt = rng.standard_normal((ch, ch, k))
+        bias = rng.standard_normal(ch)
+        x = rng.standard_normal((2, ch, Ln))
+        ref = O.conv1d(x, wt, bias, d, pad)
+        s_lo, s_hi = -((pad + P - 1) // P), ((k - 1) * d - pad + P - 1) // P
+        wf = np.zeros((P * ch, P * ch, s_hi - s_lo + 1))
+        for si, sh in enumerate(range(s_lo, s_hi + 1)):
+            for po in range(P):
+                for pi in range(P):
+                    num = P * sh + pi - po + pad
+                    if num >= 0 and num % d == 0 and num // d < k:
+                        wf[po * ch:(po + 1) * ch, pi * ch:(pi + 1) * ch, si] = wt[:, :, num // d]
+        # [B, C, L] -> folded [B, P*C, L/P] (row q holds times P q .. P q + P - 1, phase-major channels)
+        xf = x.reshape(2, ch, Ln // P, P).transpose(0, 3, 1, 2).reshape(2, P * ch, Ln // P)
+        yf = O.conv1d(xf, wf, np.tile(bias, P), 1, -s_lo)
+        assert s_hi == -s_lo  # odd kernels with "same" padding fold symmetrically
+        y = yf.reshape(2, P, ch, Ln // P).transpose(0, 2, 3, 1).reshape(2, ch, Ln)
+        np.testing.assert_allclose(y, ref, atol=1e-12)
+
+
 def test_no_product_import_of_oracle():
     """The oracle is test infrastructure: nothing under the package may import it."""
     pkg = os.path.join(ROOT, "svc_inference_pipeline_b200")
