@@ -43,7 +43,7 @@ AMP_ELEMS_PER_FRAME = 614_400  # Activation1d elements per mel frame over the 10
 
 def load_traffic(precision, kernel):
     """DRAM bytes per launch of a kernel class from the committed ncu launch list (None if absent)."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic_v14.json")
+    path = os.path.join(ROOT, "profiles", "r01_traffic_v18.json")
     try:
         return json.load(open(path))[precision][kernel]["dram_bytes_per_launch"]
     except Exception:

@@ -3,7 +3,7 @@
 # bench shape for both precisions, and --set full captures of three kernels of the fp32 path
 # (wide conv, narrow conv, Activation1d).  Usage: tools/gpu_ncu_round.sh <tag>
 set -u
-TAG=${1:-v7}
+TAG=${1:-v18}
 OUT=gpurun_out
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
 for P in fp32 bf16; do
