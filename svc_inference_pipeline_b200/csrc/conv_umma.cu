@@ -15,12 +15,15 @@
 //         are zero-filled by TMA (a 3-D map [B][L][C] keeps batch items apart) = Conv1d padding.
 //      B: one [n_tile x 64ch] box of the packed weights per (tap, Cin slice).
 //  * tcgen05.mma (cta_group::1, kind::f16, M=128, N=n_tile, K=16) issued by one thread,
-//    accumulating in TMEM; two accumulator stages so the epilogue of tile i overlaps tile i+1;
+//    accumulating in TMEM; a tile is mb row blocks of 128 sharing every weight box, with as many
+//    accumulator stages as fit in the 512 columns so the epilogue of tile i overlaps tile i+1;
 //  * SPLIT operands (fp32-parity path): A and W come as (hi, lo) bf16 planes and each K slice
-//    issues hi*hi + lo*hi + hi*lo (3 MMAs, fp32 accumulate): 16 mantissa bits per operand;
+//    issues hi*hi + lo*hi + hi*lo (3 MMAs, fp32 accumulate): 16 mantissa bits per operand
+//    (narrow layers: [W_hi; W_lo] stacked along N, 2 MMAs);
 //  * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-//    warps 4-7 = epilogue (tcgen05.ld 32 lanes x 32 columns -> bias/residual/accumulate/divide
-//    -> F32 | BF16 | SPLIT stores).  Persistent: grid = min(#tiles, #SMs), static round-robin.
+//    warps 4-11 = epilogue (tcgen05.ld -> swizzled staging -> bias/residual/accumulate/divide
+//    -> F32 | BF16 | SPLIT stores), fused mode: warps 12-19 = Activation1d operand producer.
+//    Persistent: grid = min(#tiles, #SMs), static round-robin.
 //
 // Every mbarrier wait is bounded: a pipeline bug traps (launch failure) instead of hanging the GPU.
 #include <cuda.h>
