@@ -318,3 +318,32 @@ def test_fused_activation_layers_match_unfused(repo_model):
     assert len(fused) == 18 and len(fused_all) == 36, (len(fused), len(fused_all))
     assert float((y_fused - y_plain).abs().max()) < 2e-6
     assert float((y_fused_all - y_plain).abs().max()) < 2e-6
+
+
+def test_full_size_properties(repo_model):
+    """BASELINE configs[1] at its full size (batch 16 x 938 frames, the bench shape; the oracle needs minutes per
+    item there): size-independent properties instead -- every batch item is independent of its neighbours, a chunk
+    with a 48-frame halo reproduces the interior of the full forward, the waveform is finite and inside tanh's
+    range, and the bf16 path stays within its SNR gate of the fp32 path."""
+    from svc_inference_pipeline_b200.utils import synth
+
+    m = repo_model
+    mel = torch.from_numpy(synth.synthetic_mel(16, 100, 938, seed=1235)).to(DEV)
+    full = m(mel)
+    assert full.shape == (16, 1, 938 * 256)
+    assert torch.isfinite(full).all() and full.abs().max().item() <= 1.0
+    for b in (0, 7, 15):
+        single = m(mel[b : b + 1].contiguous())
+        assert (full[b : b + 1] - single).abs().max().item() < 2e-6, b
+    lo, hi, halo = 400, 520, 48
+    part = m(mel[3:5, :, lo - halo : hi + halo].contiguous())
+    a = full[3:5, 0, lo * 256 : hi * 256]
+    c = part[:, 0, halo * 256 : (halo + hi - lo) * 256]
+    assert (a - c).abs().max().item() < 5e-6
+    try:
+        m.set_precision("bf16")
+        yb = m(mel)
+    finally:
+        m.set_precision("fp32")
+    snr = 10 * np.log10(float((full.double() ** 2).sum() / ((yb - full).double() ** 2).sum()))
+    assert snr > 35.0, snr
