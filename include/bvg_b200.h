@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BVG_ABI_VERSION 2  /* 2: bvg_conv_geom.fold, bvg_conv_desc.pre_amp */
+#define BVG_ABI_VERSION 3  /* 2: bvg_conv_geom.fold, bvg_conv_desc.pre_amp; 3: bvg_stitch_fwd */
 
 enum bvg_status {
   BVG_OK = 0,
@@ -212,6 +212,30 @@ typedef struct bvg_tail_desc {
 } bvg_tail_desc;
 
 int bvg_tail_fwd(const bvg_tail_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Cross-fade stitch of time chunks (the reference vocodes one whole utterance per
+ * forward, modules/bigvgan_inference.py:34-36, and has no chunking -- this is the "cross-fades the chunks"
+ * step of the long-form path).  d_wave holds the generator outputs of n_chunks equal-length input
+ * windows (one batch, row stride wave_stride floats).  Row j of d_table = {dst, src, n, fade_in,
+ * fade_out} (int64): samples src .. src+n-1 of chunk j go to d_out[dst ..], the first fade_in of them
+ * ramped up with weight (i + 0.5) / fade_in, the last fade_out ramped down with 1 - (i + 0.5) / fade_out.
+ * The body is stored, the two fade windows are ADDED to what d_out holds (the neighbour's half of the
+ * blend, or zero: d_out must be zero-filled before the first chunk of a span).  Neighbouring chunks of
+ * one call overlap in their fade windows, so the call runs the even and the odd rows as two launches.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct bvg_stitch_desc {
+  const float* d_wave;
+  int64_t wave_stride;
+  float* d_out;
+  int64_t out_len;        /* bound check: dst + n <= out_len for every row */
+  const int64_t* d_table; /* DEVICE [n_chunks][5] */
+  const int64_t* h_table; /* HOST copy of the same table (validated here; the device is not read back) */
+  int32_t n_chunks;
+  int32_t _pad;
+} bvg_stitch_desc;
+
+int bvg_stitch_fwd(const bvg_stitch_desc* d, void* stream);
 
 /* Layout/format helpers used by tests and by the sharded stitch. */
 int bvg_convert(const bvg_tensor* src, const bvg_tensor* dst, size_t n_elems, void* stream);

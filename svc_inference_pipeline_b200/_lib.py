@@ -16,6 +16,7 @@ F32, BF16, SPLIT = 0, 1, 2
 SIMT, UMMA = 0, 1
 OP_PACK, OP_AMP, OP_CONV, OP_POST = 0, 1, 2, 3
 MAX_TAPS, MAX_NTILES = 16, 32
+ABI_VERSION = 3
 
 
 class BvgError(RuntimeError):
@@ -130,6 +131,19 @@ class TailDesc(C.Structure):
     ]
 
 
+class StitchDesc(C.Structure):
+    _fields_ = [
+        ("d_wave", C.c_void_p),
+        ("wave_stride", C.c_int64),
+        ("d_out", C.c_void_p),
+        ("out_len", C.c_int64),
+        ("d_table", C.c_void_p),
+        ("h_table", C.c_void_p),
+        ("n_chunks", C.c_int32),
+        ("_pad", C.c_int32),
+    ]
+
+
 class _OpUnion(C.Union):
     _fields_ = [("pack", PackDesc), ("amp", AmpDesc), ("conv", ConvDesc), ("post", PostDesc)]
 
@@ -156,6 +170,7 @@ EXPORTS = [
     "bvg_pack_post_weights",
     "bvg_pack_mel",
     "bvg_tail_fwd",
+    "bvg_stitch_fwd",
     "bvg_convert",
     "bvg_program_create",
     "bvg_program_run",
@@ -190,6 +205,7 @@ def lib():
         "bvg_post_fwd": [C.POINTER(PostDesc), C.c_void_p],
         "bvg_pack_mel": [C.POINTER(PackDesc), C.c_void_p],
         "bvg_tail_fwd": [C.POINTER(TailDesc), C.c_void_p],
+        "bvg_stitch_fwd": [C.POINTER(StitchDesc), C.c_void_p],
         "bvg_convert": [C.POINTER(Tensor), C.POINTER(Tensor), C.c_size_t, C.c_void_p],
         "bvg_conv_geometry": [C.POINTER(ConvGeom), C.POINTER(ConvWeights)],
         "bvg_conv_pack_bytes": [C.POINTER(ConvGeom), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)],
@@ -205,8 +221,8 @@ def lib():
         fn = getattr(L, name)
         fn.argtypes = argtypes
         fn.restype = None if name == "bvg_program_destroy" else C.c_int
-    if L.bvg_abi_version() != 2:
-        raise BvgError(f"ABI mismatch: library reports version {L.bvg_abi_version()}, binding expects 2")
+    if L.bvg_abi_version() != ABI_VERSION:
+        raise BvgError(f"ABI mismatch: library reports version {L.bvg_abi_version()}, binding expects {ABI_VERSION}")
     if L.bvg_sizeof_op() != C.sizeof(Op) or L.bvg_sizeof_conv_weights() != C.sizeof(ConvWeights):
         raise BvgError(
             f"struct layout mismatch: C sizeof(bvg_op)={L.bvg_sizeof_op()} vs ctypes {C.sizeof(Op)}; "

@@ -395,11 +395,8 @@ static cudaError_t launch_amp_p2_ct(const AmpParams& p, cudaStream_t st) {
   const long long blocks = ceil_div_ll(p.total_threads, threads);
   // Same shared-memory carve-out as the convolution kernel (max shared): an SM can only host kernels of
   // two streams at once when they agree on the L1 / shared split, and this kernel streams through L2 anyway.
-  static bool configured = false;
-  if (!configured) {
+  if (first_use_on_device(reinterpret_cast<const void*>(amp_kernel_p2<IN_BF16, OUT_MODE, FAST_SIN, CT>)))
     cudaFuncSetAttribute(amp_kernel_p2<IN_BF16, OUT_MODE, FAST_SIN, CT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    configured = true;
-  }
   amp_kernel_p2<IN_BF16, OUT_MODE, FAST_SIN, CT><<<(unsigned)blocks, threads, 0, st>>>(p);
   return cudaGetLastError();
 }

@@ -1,6 +1,9 @@
 // extern "C" surface of libbvg_b200.so (see include/bvg_b200.h) and the program runner.
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <set>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -22,6 +25,15 @@ int cuda_fail(cudaError_t e, const char* what) {
   return BVG_ECUDA;
 }
 
+bool first_use_on_device(const void* kernel) {
+  static std::mutex mu;
+  static std::set<std::pair<int, const void*>> seen;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  return seen.insert(std::make_pair(dev, kernel)).second;
+}
+
 // kernels (defined in the other translation units)
 int amp_forward(const bvg_amp_desc* d, cudaStream_t st);
 int conv_simt_forward(const bvg_conv_desc* d, cudaStream_t st);
@@ -29,6 +41,7 @@ int conv_umma_forward(const bvg_conv_desc* d, cudaStream_t st);
 int post_forward(const bvg_post_desc* d, cudaStream_t st);
 int pack_mel(const bvg_pack_desc* d, cudaStream_t st);
 int tail_forward(const bvg_tail_desc* d, cudaStream_t st);
+int stitch_forward(const bvg_stitch_desc* d, cudaStream_t st);
 int convert(const bvg_tensor* src, const bvg_tensor* dst, size_t n, cudaStream_t st);
 int conv_geometry(const bvg_conv_geom* g, bvg_conv_weights* w);
 size_t conv_plane_elems(const bvg_conv_weights* w);
@@ -114,6 +127,7 @@ int bvg_conv_fwd(const bvg_conv_desc* d, void* stream) { return bvg::conv_forwar
 int bvg_post_fwd(const bvg_post_desc* d, void* stream) { return bvg::post_forward(d, (cudaStream_t)stream); }
 int bvg_pack_mel(const bvg_pack_desc* d, void* stream) { return bvg::pack_mel(d, (cudaStream_t)stream); }
 int bvg_tail_fwd(const bvg_tail_desc* d, void* stream) { return bvg::tail_forward(d, (cudaStream_t)stream); }
+int bvg_stitch_fwd(const bvg_stitch_desc* d, void* stream) { return bvg::stitch_forward(d, (cudaStream_t)stream); }
 int bvg_convert(const bvg_tensor* src, const bvg_tensor* dst, size_t n, void* stream) {
   return bvg::convert(src, dst, n, (cudaStream_t)stream);
 }

@@ -30,6 +30,10 @@ int cuda_fail(cudaError_t e, const char* what);
     }                                 \
   } while (0)
 
+// True exactly once per (current device, kernel): function attributes (dynamic shared-memory opt-in, carve-out
+// preference) are per device, so a process that drives several GPUs must set them on each.  Thread-safe.
+bool first_use_on_device(const void* kernel);
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 

@@ -1085,15 +1085,9 @@ static UmmaKernel select_kernel(const UmmaParams& p) {
 int conv_umma_launch(const UmmaLaunch* l, cudaStream_t st) {
   if (l->grid <= 0) return BVG_OK;
   UmmaKernel k = select_kernel(l->p);
-  // opt in to > 48 KB of dynamic shared memory once per specialisation (cheap, idempotent)
-  static UmmaKernel configured[32];
-  static int n_configured = 0;
-  bool seen = false;
-  for (int i = 0; i < n_configured; ++i) seen = seen || configured[i] == k;
-  if (!seen) {
+  // opt in to > 48 KB of dynamic shared memory once per (device, specialisation): the attribute is per device
+  if (first_use_on_device(reinterpret_cast<const void*>(k)))
     BVG_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_LIMIT));
-    if (n_configured < 32) configured[n_configured++] = k;
-  }
   k<<<l->grid, l->p.f_x ? UM_THREADS_FUSED : UM_THREADS, l->smem, st>>>(l->p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "conv_umma_kernel launch");

@@ -141,4 +141,64 @@ int tail_forward(const bvg_tail_desc* d, cudaStream_t st) {
   return BVG_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Cross-fade stitch of time chunks (see bvg_stitch_desc): one thread per four samples of a chunk's kept range.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stitch_kernel(const float* __restrict__ wave, long long wave_stride, float* __restrict__ out,
+                                                     const long long* __restrict__ table, int first, int step, int blocks_per_chunk) {
+  const int j = first + step * (int)(blockIdx.x / blocks_per_chunk);
+  const long long* row = table + 5ll * j;
+  const long long dst = row[0], src = row[1], n = row[2], fin = row[3], fout = row[4];
+  const float* w = wave + (long long)j * wave_stride + src;
+  float* o = out + dst;
+  const long long per = (long long)blockDim.x * 4;
+  for (long long i0 = ((long long)(blockIdx.x % blocks_per_chunk) * blockDim.x + threadIdx.x) * 4; i0 < n; i0 += per * blocks_per_chunk) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long i = i0 + k;
+      if (i >= n) break;
+      float v = w[i];
+      if (i < fin) {
+        v = __fmul_rn(v, __fdiv_rn(__fadd_rn((float)i, 0.5f), (float)fin));
+        o[i] = __fadd_rn(o[i], v);
+      } else if (i >= n - fout) {
+        const long long r = i - (n - fout);
+        v = __fmul_rn(v, __fsub_rn(1.0f, __fdiv_rn(__fadd_rn((float)r, 0.5f), (float)fout)));
+        o[i] = __fadd_rn(o[i], v);
+      } else {
+        o[i] = v;
+      }
+    }
+  }
+}
+
+int stitch_forward(const bvg_stitch_desc* d, cudaStream_t st) {
+  BVG_REQUIRE(d && d->d_wave && d->d_out && d->d_table && d->h_table, "stitch: null pointer");
+  BVG_REQUIRE(d->n_chunks > 0 && d->wave_stride > 0 && d->out_len > 0, "stitch: bad shape");
+  long long max_n = 0;
+  for (int j = 0; j < d->n_chunks; ++j) {
+    const int64_t* r = d->h_table + 5ll * j;
+    BVG_REQUIRE(r[0] >= 0 && r[1] >= 0 && r[2] > 0 && r[3] >= 0 && r[4] >= 0, "stitch: row %d has a negative entry", j);
+    BVG_REQUIRE(r[0] + r[2] <= d->out_len && r[1] + r[2] <= d->wave_stride, "stitch: row %d leaves its buffers", j);
+    BVG_REQUIRE(r[3] + r[4] <= r[2], "stitch: row %d fades %lld + %lld samples of %lld", j, (long long)r[3], (long long)r[4], (long long)r[2]);
+    if (j + 1 < d->n_chunks) {  // rows two apart must not overlap (they run in the same launch)
+      const int64_t* q = d->h_table + 5ll * (j + 1);
+      // whatever rows j and j+1 share of d_out lies inside j's fade-out window and inside j+1's fade-in window
+      BVG_REQUIRE(q[0] >= r[0] + r[2] - r[4] && r[0] + r[2] <= q[0] + q[3],
+                  "stitch: rows %d and %d are not consecutive chunks overlapping only in their fade windows", j, j + 1);
+      if (j + 2 < d->n_chunks) BVG_REQUIRE((d->h_table + 5ll * (j + 2))[0] >= r[0] + r[2], "stitch: rows %d and %d overlap", j, j + 2);
+    }
+    if (r[2] > max_n) max_n = r[2];
+  }
+  int bpc = (int)ceil_div_ll(max_n, 256 * 4 * 4);
+  if (bpc < 1) bpc = 1;
+  if (bpc > 4096) bpc = 4096;
+  for (int first = 0; first < 2 && first < d->n_chunks; ++first) {
+    const int count = (d->n_chunks - first + 1) / 2;
+    stitch_kernel<<<(unsigned)(count * bpc), 256, 0, st>>>(d->d_wave, d->wave_stride, d->d_out, reinterpret_cast<const long long*>(d->d_table), first, 2, bpc);
+    BVG_CHECK_CUDA(cudaGetLastError());
+  }
+  return BVG_OK;
+}
+
 }  // namespace bvg

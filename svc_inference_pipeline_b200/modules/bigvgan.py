@@ -255,6 +255,7 @@ class Generator(nn.Module):
         self.hop = int(math.prod(cfg.upsample_rates))
         self._packed = None
         self._programs: "OrderedDict[tuple, _Program]" = OrderedDict()
+        self._batch_bufs = {}  # whole-batch (mel, waveform) buffers of the overlapped forward, keyed like the programs
         self.max_cached_programs = 6
         # narrow resblock convolutions read four rows as one (see _time_fold); set False + _invalidate() to compare
         self.time_fold = True
@@ -277,6 +278,7 @@ class Generator(nn.Module):
     def _invalidate(self):
         self._packed = None
         self._programs.clear()
+        self._batch_bufs.clear()
 
     def _apply(self, fn, *args, **kwargs):
         self._invalidate()
@@ -308,6 +310,7 @@ class Generator(nn.Module):
             rng = (mx - mn + np.float32(1e-12)).astype(np.float32)  # float32 array + python float stays float32
             self._mel_denorm = (torch.from_numpy(rng), torch.from_numpy(mn))
         self._programs.clear()
+        self._batch_bufs.clear()
         return self
 
     def remove_weight_norm(self):
@@ -413,13 +416,20 @@ class Generator(nn.Module):
             return m.cout % 8 == 0
         return m.cin % 8 == 0 and (m.cout % 8 == 0)
 
+    def receptive_field_frames(self) -> int:
+        """One-sided receptive field in mel frames, derived from the hyper-parameters (``sharding.receptive_field_frames``):
+        the halo a time chunk needs.  38 for the repo config."""
+        from ..sharding import receptive_field_frames
+
+        return receptive_field_frames(self.cfg)
+
     def packed_weight_bytes(self) -> int:
         if self._packed is None:
             self._pack()
         return sum(p.nbytes() for p in self._packed["conv"].values())
 
     # -- program construction ---------------------------------------------------------------------
-    def _build_program(self, B: int, T: int) -> _Program:
+    def _build_program(self, B: int, T: int, mel_in=None, out=None) -> _Program:
         if self._packed is None:
             self._pack()
         dev = self._device()
@@ -470,7 +480,9 @@ class Generator(nn.Module):
 
         def amp_conv(aname, x, cname, out, B_, L_, C_, **epi):
             """Activation1d -> convolution: one kernel when the layer qualifies (_fuse_amp), else the pair through t_op."""
-            if self._fuse_amp(cname, x):
+            # never when the output buffer is the Activation1d's own input (AMPBlock2 after the first layer: xa -> xa):
+            # the fused producer reads halo rows of x that other CTAs are overwriting as output
+            if self._fuse_amp(cname, x) and out is not x:
                 conv_op(cname, None, out, B_, L_, pre_amp=(aname, x), **epi)
             else:
                 amp_op(aname, x, t_op, B_, L_, C_)
@@ -499,7 +511,8 @@ class Generator(nn.Module):
             chans.append(c0 // 2 ** (i + 1))
         max_elems = max(B * l * c for l, c in zip(lens, chans))
 
-        mel_in = torch.empty(B, cfg.input_dim, T, dtype=torch.float32, device=dev)
+        if mel_in is None:  # else: the caller's slice of a whole-batch staging buffer (overlapped forward)
+            mel_in = torch.empty(B, cfg.input_dim, T, dtype=torch.float32, device=dev)
         pre = pk["conv"]["conv_pre"]
         melp = _Buf(op_dt, B * T * pre.x_pitch, dev)
         h = _Buf(op_dt, max(B * T * c0, max_elems), dev)        # operand-format stage input (ping)
@@ -510,7 +523,9 @@ class Generator(nn.Module):
         t_op = _Buf(op_dt, max_elems, dev)
         t_mid = _Buf(mid_dt, max_elems, dev)
         y_post = _Buf(st_dt, B * lens[-1] * chans[-1], dev)
-        out = torch.empty(B, 1, lens[-1], dtype=torch.float32, device=dev)
+        if out is None:
+            out = torch.empty(B, 1, lens[-1], dtype=torch.float32, device=dev)
+        assert mel_in.is_contiguous() and out.is_contiguous() and tuple(out.shape) == (B, 1, lens[-1])
         keep += [mel_in, melp, h, h2, x_in, xa, xs, t_op, t_mid, y_post, out]
 
         labels.append(("pack_mel", "pack", 0.0))
@@ -578,13 +593,14 @@ class Generator(nn.Module):
         prog.descs = descs  # ctypes descriptors the ops point to
         return prog
 
-    def _program(self, B: int, T: int, slot: int = -1) -> _Program:
-        # slot >= 0: one of the two half-batch programs of the overlapped forward (own workspace each)
+    def _program(self, B: int, T: int, slot: int = -1, mel_in=None, out=None) -> _Program:
+        # slot >= 0: one of the half-batch programs of the overlapped forward (own workspace each; mel_in / out are
+        # its slices of the whole-batch buffers, slot = (whole batch, part index))
         key = (B, T, self.precision, slot)
         prog = self._programs.get(key)
         if prog is None:
             with torch.cuda.device(self._device()):
-                prog = self._build_program(B, T)
+                prog = self._build_program(B, T, mel_in=mel_in, out=out)
             self._programs[key] = prog
             while len(self._programs) > self.max_cached_programs:
                 self._programs.popitem(last=False)
@@ -639,6 +655,15 @@ class Generator(nn.Module):
     # -- forward ----------------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """Reference ``modules/bigvgan.py:600-622``.  The returned tensor is the caller's (a copy of the program's
+        output buffer, which the next forward of the same shape overwrites)."""
+        return self.forward_borrowed(x).clone()
+
+    @torch.no_grad()
+    def forward_borrowed(self, x: torch.Tensor) -> torch.Tensor:
+        """``forward`` without the final device copy: returns the program's own output buffer, valid until the next
+        forward of the same shape.  For callers that consume it at once (``vocoder_inference`` copies it to the
+        host, ``synthesis_pcm16`` quantises it)."""
         dev = self._require_cuda()
         if x.dim() != 3 or x.shape[1] != self.cfg.input_dim:
             raise ValueError(f"expected mel of shape [B, {self.cfg.input_dim}, T], got {tuple(x.shape)}")
@@ -662,7 +687,7 @@ class Generator(nn.Module):
                 prog.graph.replay()
             else:
                 prog.run(stream.cuda_stream)
-            return prog.out.clone()
+            return prog.out
 
     def _forward_overlapped(self, x: torch.Tensor, dev) -> torch.Tensor:
         B, _, T = x.shape
@@ -670,12 +695,24 @@ class Generator(nn.Module):
         cuts = [(B * k + n - 1) // n for k in range(n + 1)]
         parts = [(cuts[k], cuts[k + 1]) for k in range(n)]
         with torch.cuda.device(dev):
-            progs = [self._program(hi - lo, T, slot=k) for k, (lo, hi) in enumerate(parts)]
+            # whole-batch staging buffers; every part's program reads / writes its own slice of them, so one copy
+            # brings the mels in and the waveform of the batch is contiguous without a concatenation
+            bkey = (B, T, self.precision, "batch", n)
+            bufs = self._batch_bufs.get(bkey)
+            if bufs is None:
+                if len(self._batch_bufs) >= self.max_cached_programs:
+                    self._batch_bufs.clear()
+                    self._programs.clear()
+                bufs = (torch.empty(B, self.cfg.input_dim, T, dtype=torch.float32, device=dev), torch.empty(B, 1, T * self.hop, dtype=torch.float32, device=dev))
+                self._batch_bufs[bkey] = bufs
+            mel_all, out_all = bufs
+            progs = [self._program(hi - lo, T, slot=(B, n, k), mel_in=mel_all[lo:hi], out=out_all[lo:hi]) for k, (lo, hi) in enumerate(parts)]
+            if any(pr.mel_in.data_ptr() != mel_all[lo:hi].data_ptr() for pr, (lo, hi) in zip(progs, parts)):
+                raise RuntimeError("overlapped forward: cached part programs do not belong to the batch buffers")
             if self._side_streams is None or len(self._side_streams) != n or self._side_streams[0].device != dev:
                 self._side_streams = [torch.cuda.Stream(device=dev) for _ in range(n)]
             cur = torch.cuda.current_stream(dev)
-            for prog, (lo, hi) in zip(progs, parts):
-                prog.mel_in.copy_(x[lo:hi], non_blocking=True)
+            mel_all.copy_(x, non_blocking=True)
             ready = cur.record_event()
             for st in self._side_streams:
                 st.wait_event(ready)
@@ -684,4 +721,4 @@ class Generator(nn.Module):
             L.check(L.lib().bvg_program_run_interleaved(handles, streams, n), "program_run_interleaved")
             for st in self._side_streams:
                 cur.wait_event(st.record_event())
-            return torch.cat([pr.out for pr in progs], dim=0)
+            return out_all

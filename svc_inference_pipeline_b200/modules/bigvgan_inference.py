@@ -25,7 +25,9 @@ def vocoder_inference(cfg, model, mels, device, fast_inference=False):
     model.eval()
     with torch.no_grad():
         mels = mels.to(device)
-        output = model.forward(mels)
+        # the B200 Generator hands out its own output buffer here (no device-side copy): .cpu() below is the
+        # consumer and is synchronous; any other model goes through forward() like in the reference
+        output = getattr(model, "forward_borrowed", model.forward)(mels)
     return output.squeeze(1).detach().cpu()
 
 
@@ -51,7 +53,7 @@ def synthesis_pcm16(model, mel, cfg, add_silence=True, turn_up=True, volume_peak
     B, _, frames = mels.shape
     model.eval()
     with torch.no_grad():
-        wave = model.forward(mels.to(device))  # [B, 1, T*hop] fp32 on the device
+        wave = getattr(model, "forward_borrowed", model.forward)(mels.to(device))  # [B, 1, T*hop] fp32 on the device
     Ln = frames * cfg.hop_length
     fade = 20 * cfg.hop_length
     if fade > Ln:

@@ -96,7 +96,9 @@ def golden_activation():
     out["big_x"] = xb
     out["big_alpha"] = act.alpha.numpy().copy()
     out["big_beta"] = act.beta.numpy().copy()
-    out["big_y"] = ref.Activation1d(activation=act)(torch.from_numpy(xb)).numpy()
+    a1d_big = ref.Activation1d(activation=act)
+    out["big_y"] = a1d_big(torch.from_numpy(xb)).numpy()
+    out["big_y_f64"] = a1d_big.double()(torch.from_numpy(xb).double()).numpy()  # shows the reference's own fp32 noise at |a u| ~ 1e2
     save("activation1d.npz", **out)
 
 
@@ -224,11 +226,99 @@ def mel_range_fixture():
     print("wrote", path)
 
 
+def _repo_vcfg():
+    cfg = load_config(os.path.join(REF, "config", "config.json"))
+    return {k: cfg.vocoder[k] for k in TINY}
+
+
+def golden_bench_item():
+    """The BENCHMARKED shape (BASELINE configs[1], bench.py): item 7 of the B16 x 938-frame batch bench.py feeds
+    rank 0 (synthetic_mel(16, 100, 938, seed=1235)), through the unmodified reference in fp32 and fp64.  The mel is
+    regenerated by the tests (its sha256 is stored); fp64 is stored as float32(y_f64) + the fp32 reference."""
+    vcfg = _repo_vcfg()
+    model, _ = load_into_reference(vcfg, seed=0)
+    item = 7
+    mel = synth.synthetic_mel(16, 100, 938, seed=1235)[item : item + 1]
+    y32 = model(torch.from_numpy(mel)).numpy()
+    y64 = model.double()(torch.from_numpy(mel).double()).numpy()
+    save("bench_item.npz", item=item, batch=16, frames=938, seed=1235, mel_sha256=np.frombuffer(hashlib.sha256(mel.tobytes()).digest(), dtype=np.uint8),
+         y=y32, y_f64=y64, ref_fp32_vs_fp64=np.abs(y32 - y64).max())
+
+
+def golden_v2_long():
+    """BASELINE configs[4] length class: one 30-s item ([1, 128, 2584], hop 512) of the 512x v2 generator: item 3 of
+    the batch tools/time_forward.py --v2 and bench.py's v2 leg use (synthetic_mel(8, 128, 2584, seed=1235)).  The
+    waveform has 1.32 M samples, so only float32(reference fp64) is stored, with the reference's own fp32-vs-fp64
+    distance next to it."""
+    vcfg = dict(_repo_vcfg(), input_dim=128, upsample_rates=[8, 4, 2, 2, 2, 2], upsample_kernel_sizes=[16, 8, 4, 4, 4, 4])
+    model, _ = load_into_reference(vcfg, seed=0)
+    item = 3
+    mel = synth.synthetic_mel(8, 128, 2584, seed=1235)[item : item + 1]
+    y32 = model(torch.from_numpy(mel)).numpy()
+    y64 = model.double()(torch.from_numpy(mel).double()).numpy()
+    save("v2_long.npz", item=item, batch=8, frames=2584, seed=1235, mel_sha256=np.frombuffer(hashlib.sha256(mel.tobytes()).digest(), dtype=np.uint8),
+         y_f64_as_f32=y64.astype(np.float32), ref_fp32_vs_fp64=np.abs(y32 - y64).max(), ref_fp32_snr_db=10 * np.log10((y64**2).sum() / ((y32 - y64) ** 2).sum()))
+
+
+def golden_recipes():
+    """Repo generator under the two other checkpoint recipes of utils/synth.py (RECIPES): SURVEY.md section 8d as written
+    ("survey") and trained-like large snake frequencies ("large_alpha"), 96 log-mel frames each, fp32 + fp64."""
+    vcfg = _repo_vcfg()
+    out = {}
+    mel = synth.synthetic_mel(1, 100, 96, seed=1240)
+    out["mel"] = mel
+    for recipe in ("survey", "large_alpha"):
+        vc = JsonHParams(**vcfg)
+        model = ref.Generator(vc).eval()
+        sd = synth.synthetic_state_dict(vcfg, 0, recipe=recipe)
+        model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        y32 = model(torch.from_numpy(mel)).numpy()
+        y64 = model.double()(torch.from_numpy(mel).double()).numpy()
+        out[recipe + "_y"], out[recipe + "_y_f64"] = y32, y64
+        print(f"{recipe}: reference fp32 vs fp64 max-abs {np.abs(y32 - y64).max():.3e}, |y|max {np.abs(y64).max():.3f}")
+    save("recipes.npz", **out)
+
+
+def golden_logmel():
+    """The reference's log-mel analysis (utils/mel.py:130-174) run UNMODIFIED.  Its mel basis comes from librosa
+    (absent here, unpinned by the reference); oracle/logmel_oracle.py restates librosa.filters.mel and is supplied in
+    its place, after being checked against the independent implementation in transformers.audio_utils."""
+    import types
+
+    from oracle import logmel_oracle as LM
+
+    fb = LM.slaney_mel_filterbank(24000, 1024, 100, 0, 12000)
+    try:
+        from transformers.audio_utils import mel_filter_bank
+
+        other = mel_filter_bank(num_frequency_bins=513, num_mel_filters=100, min_frequency=0.0, max_frequency=12000.0, sampling_rate=24000, norm="slaney", mel_scale="slaney").T
+        dev = np.abs(other - fb).max()
+        print(f"slaney filterbank vs transformers.audio_utils.mel_filter_bank: max-abs {dev:.3e} (peak weight {fb.max():.3e})")
+        assert dev < 1e-6 * max(1.0, fb.max())
+    except ImportError:
+        print("transformers not importable: filterbank restatement not cross-checked")
+    librosa = types.ModuleType("librosa")
+    librosa.filters = types.ModuleType("librosa.filters")
+    librosa.filters.mel = lambda sr, n_fft, n_mels, fmin, fmax: LM.slaney_mel_filterbank(sr, n_fft, n_mels, fmin, fmax)
+    audio_stub = types.ModuleType("utils.audio")  # utils/mel.py:13 imports the WAV loader (needs soundfile); unused by mel_spectrogram
+    audio_stub.load_audio_torch = None
+    sys.modules.update({"librosa": librosa, "librosa.filters": librosa.filters, "utils.audio": audio_stub})
+    from utils import mel as ref_mel  # the reference, unmodified
+
+    rng = np.random.Generator(np.random.PCG64(5))
+    t = np.arange(24000 * 2) / 24000.0
+    wave = (0.3 * np.sin(2 * np.pi * (220 + 200 * t) * t) + 0.1 * np.sin(2 * np.pi * 3100 * t) + 0.02 * rng.standard_normal(t.size)).astype(np.float32)
+    wave[30000:33000] = 0.0  # a silent stretch: exercises the 1e-5 clip
+    m = ref_mel.mel_spectrogram(torch.from_numpy(wave)[None], 1024, 100, 24000, 256, 1024, 0, 12000, center=False).numpy()
+    save("logmel.npz", wave=wave, logmel=m, basis=fb)
+
+
+STEPS = {
+    "mel_range": mel_range_fixture, "filters": golden_filters, "activation": golden_activation, "convs": golden_convs, "tiny": golden_tiny,
+    "repo": golden_repo, "bench_item": golden_bench_item, "v2_long": golden_v2_long, "recipes": golden_recipes, "logmel": golden_logmel,
+}
+
 if __name__ == "__main__":
     torch.manual_seed(0)
-    mel_range_fixture()
-    golden_filters()
-    golden_activation()
-    golden_convs()
-    golden_tiny()
-    golden_repo()
+    for name in (sys.argv[1:] or list(STEPS)):
+        STEPS[name]()

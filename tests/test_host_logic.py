@@ -117,7 +117,7 @@ def test_capi_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/bvg_b200.h but not exported"
     assert sorted(L.EXPORTS) == names
-    assert lib.bvg_abi_version() == 2
+    assert lib.bvg_abi_version() == L.ABI_VERSION
     assert lib.bvg_sizeof_op() == C.sizeof(L.Op)
     assert lib.bvg_sizeof_conv_weights() == C.sizeof(L.ConvWeights)
 
@@ -216,3 +216,38 @@ def test_amp_mma_index_math():
     import amp_mma_emulation as E
 
     assert E.main(lengths=(1, 2, 3, 4, 7, 8, 9, 12, 13, 16, 20, 31, 32, 33, 67), verbose=False) < 1e-12
+
+
+def test_load_mel_min_max_honours_reference_config_keys(tmp_path):
+    """Reference contract (utils/acoustic_feature_extraction.py:66-72): the statistics come from the pickles named by
+    cfg.min_mel_file / cfg.max_mel_file; the shipped copy is only a fallback, and a config without them warns."""
+    import pickle
+    import warnings
+
+    import torch
+
+    from svc_inference_pipeline_b200.utils.acoustic_feature_extraction import denormalize_mel_channel, load_mel_min_max
+    from svc_inference_pipeline_b200.utils.util import JsonHParams
+
+    rng = np.random.default_rng(1)
+    lo = rng.uniform(-12, -10, 100).astype(np.float32)
+    hi = rng.uniform(-5, 1, 100).astype(np.float32)
+    for name, arr in (("mel_min.pkl", lo), ("mel_max.pkl", hi)):
+        with open(tmp_path / name, "wb") as f:
+            pickle.dump(arr, f)
+    cfg = JsonHParams(min_mel_file=str(tmp_path / "mel_min.pkl"), max_mel_file=str(tmp_path / "mel_max.pkl"))
+    got_lo, got_hi = load_mel_min_max(cfg)
+    np.testing.assert_array_equal(got_lo, lo)
+    np.testing.assert_array_equal(got_hi, hi)
+    mel = rng.uniform(-1, 1, (100, 9)).astype(np.float32)
+    ref = (mel + 1) / 2 * (np.expand_dims(hi, -1) - np.expand_dims(lo, -1) + 1e-12) + np.expand_dims(lo, -1)
+    np.testing.assert_array_equal(denormalize_mel_channel(torch.from_numpy(mel), cfg).numpy(), ref)
+    np.savez(tmp_path / "range.npz", mel_min=lo + 1, mel_max=hi + 1)
+    np.testing.assert_array_equal(load_mel_min_max(JsonHParams(mel_range_path=str(tmp_path / "range.npz")))[0], lo + 1)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        d_lo, _ = load_mel_min_max(JsonHParams(hop_length=256))
+        assert any("shipped" in str(x.message) for x in w)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        np.testing.assert_array_equal(load_mel_min_max()[0], d_lo)  # no config: the shipped copy, silently

@@ -237,3 +237,55 @@ def test_synthesis_pcm16_oracle_vs_reference_steps(tmp_path):
     save_audio(path, audio, fs)  # float input: processed on the host like the reference
     with wave.open(path) as f:
         assert f.getnframes() == audio.size + 2 * (fs // 20)
+
+
+# ------------------------------------------------------------------------------------------
+# log-mel analysis (reference utils/mel.py:130-174) and the bench-shape pins
+# ------------------------------------------------------------------------------------------
+def test_logmel_oracle_vs_reference(golden):
+    """oracle/logmel_oracle.py against the unmodified reference mel_spectrogram run by make_golden.py on a seeded
+    2-s waveform (with a silent stretch: the 1e-5 clip), and the slaney mel basis against the one committed there."""
+    from oracle import logmel_oracle as LM
+
+    g = golden("logmel.npz")
+    fb = LM.slaney_mel_filterbank(24000, 1024, 100, 0, 12000)
+    assert fb.shape == (100, 513) and fb.dtype == np.float32
+    np.testing.assert_array_equal(fb, g["basis"])
+    # slaney area normalisation: each triangle integrates to ~1 over Hz (bin width 24000 / 1024)
+    area = fb.sum(axis=1) * (24000 / 1024)
+    assert np.abs(area[5:] - 1.0).max() < 0.15 and np.abs(area[40:] - 1.0).max() < 0.05  # narrow low bands sample the triangle coarsely
+    m64 = LM.mel_spectrogram(g["wave"], dtype=np.float64)
+    assert m64.shape == g["logmel"].shape == (1, 100, 187)
+    # the reference computes in fp32: bins at the clip floor are exact, the rest agree to fp32 rounding of the STFT
+    assert np.abs(m64 - g["logmel"]).max() < 1e-4   # measured 1.3e-5
+    assert np.abs(m64 - g["logmel"]).mean() < 5e-6  # measured 4.8e-7
+    assert (g["logmel"] == np.float32(np.log(np.float32(1e-5)))).any()  # the silent stretch hits the clip
+    assert LM.log_mel_l1(g["wave"], g["wave"]) == 0.0
+    assert 0 < LM.log_mel_l1(g["wave"], g["wave"] * 1.01) < 0.011
+
+
+def test_bench_shape_golden_is_the_bench_input(golden):
+    """tests/golden/bench_item.npz belongs to the mel bench.py feeds rank 0 (item 7 of synthetic_mel(16, 100, 938, 1235))."""
+    import hashlib
+
+    g = golden("bench_item.npz")
+    mel = synth.synthetic_mel(int(g["batch"]), 100, int(g["frames"]), seed=int(g["seed"]))[int(g["item"])][None]
+    assert (int(g["batch"]), int(g["frames"]), int(g["seed"])) == (16, 938, 1235)
+    np.testing.assert_array_equal(np.frombuffer(hashlib.sha256(mel.tobytes()).digest(), dtype=np.uint8), g["mel_sha256"])
+    assert g["y"].shape == g["y_f64"].shape == (1, 1, 938 * 256)
+    assert float(g["ref_fp32_vs_fp64"]) < 1e-5 and np.abs(g["y_f64"]).max() <= 1.0
+
+
+@pytest.mark.parametrize("recipe", ["survey", "large_alpha"])
+def test_torch_cpu_port_vs_reference_on_recipes(golden, recipe):
+    """The PyTorch-CPU port (the CPU baseline bench.py times) reproduces the unmodified reference on the two other
+    checkpoint recipes of utils/synth.py, 96 log-mel frames of the full repo generator."""
+    import torch
+
+    from oracle import bigvgan_torch_cpu as port
+
+    g = golden("recipes.npz")
+    sd = {k: torch.from_numpy(v) for k, v in synth.synthetic_state_dict(REPO, 0, recipe=recipe).items()}
+    y = port.generator_forward(sd, REPO, torch.from_numpy(g["mel"])).numpy()
+    assert np.abs(y - g[recipe + "_y"]).max() < 2e-5
+    assert np.abs(y - g[recipe + "_y_f64"]).max() < 5e-5

@@ -46,7 +46,29 @@ def test_chunk_plan_covers_and_halo():
     assert S.shard_range(2, 4, 3) == (2, 2)
 
 
-@pytest.mark.parametrize("T,chunk", [(1000, 256), (517, 100), (300, 300), (90, 40)])
+def test_balanced_plan():
+    """Long-form plan: chunk count a multiple of the world size, equal lengths (+-1), one window length for all."""
+    for total, chunk, world in [(337500, 4096, 8), (1000, 256, 2), (517, 100, 3), (90, 40, 1), (60, 4096, 4), (25, 10, 2)]:
+        chunks = S.balanced_plan(total, chunk, halo=48, fade_frames=20, world=world)
+        assert chunks[0].start == 0 and chunks[-1].end == total
+        assert all(a.end == b.start for a, b in zip(chunks, chunks[1:]))
+        lens = [c.end - c.start for c in chunks]
+        assert max(lens) - min(lens) <= 1 and max(lens) < max(chunk + 1, 40) and min(lens) >= min(20, total)
+        assert len({c.in_hi - c.in_lo for c in chunks}) == 1
+        if total >= world * 20:
+            assert len(chunks) % world == 0
+        for c in chunks:
+            assert 0 <= c.in_lo <= c.keep_lo <= c.start < c.end <= c.keep_hi <= c.in_hi <= total
+            assert c.in_lo == 0 or c.in_lo <= c.start - 48
+            assert c.in_hi == total or c.in_hi >= c.end + 48
+    hour = S.balanced_plan(337500, 4096, world=8)
+    assert len(hour) == 88 and hour[0].in_hi - hour[0].in_lo == 3836 + 96
+    with pytest.raises(ValueError):
+        S.balanced_plan(1000, 256, halo=40, fade_frames=20)
+    S.balanced_plan(1000, 256, halo=40, fade_frames=20, receptive_field=21)  # the 512x generator's field fits
+
+
+@pytest.mark.parametrize("T,chunk", [(1000, 256), (517, 100), (300, 300), (90, 40), (30, 8)])
 def test_chunked_equals_unchunked(T, chunk):
     model = ToyVocoder()
     mel = torch.randn(6, T, generator=torch.Generator().manual_seed(1)).double()
@@ -105,3 +127,36 @@ def test_distributed_gloo(world, T, chunk, B):
         err_long, err_batch, shp, shpb = ret[r]
         assert shp == (T * HOP,) and shpb == (B, 50 * HOP)
         assert err_long < 1e-6 and err_batch < 1e-6  # the gather buffer is fp32
+
+
+@pytest.mark.parametrize("variant", ["b1_snakebeta_log", "b2_snake_lin"])
+def test_receptive_field_from_cfg(variant):
+    """sharding.receptive_field_frames(cfg) is exact: the gradient of one output sample of the PyTorch-CPU port
+    with respect to the mel is non-zero in frames [f - rf, f + rf] and nowhere else, and reaches both ends.  38 for the repo generator (the value
+    SURVEY.md appendix A measured on the reference with fp64 autograd), 21 for the 512x v2 generator."""
+    import numpy as np
+
+    from oracle import bigvgan_torch_cpu as port
+    from svc_inference_pipeline_b200.sharding import RECEPTIVE_FIELD_FRAMES, receptive_field_frames
+    from util_cases import REPO, V2, tiny_cfg_sd
+
+    assert receptive_field_frames(REPO) == RECEPTIVE_FIELD_FRAMES == 38
+    assert receptive_field_frames(V2) == 21
+    cfg, sd = tiny_cfg_sd(variant)
+    rf = receptive_field_frames(cfg)
+    hop = int(np.prod(cfg["upsample_rates"]))
+    sd = {k: torch.from_numpy(v).double() for k, v in sd.items()}
+    T, f0 = 2 * rf + 21, rf + 10
+    # structural support by autograd (a perturbation test underestimates it: the outermost paths run through the
+    # 0.002-sized end taps of every anti-aliasing filter and vanish below fp64 resolution of the output)
+    lo, hi = [], []
+    for t in (f0 * hop, f0 * hop + hop - 1):
+        mel = torch.randn(1, cfg["input_dim"], T, dtype=torch.float64, generator=torch.Generator().manual_seed(3)).requires_grad_(True)
+        with torch.enable_grad():
+            y = port.generator_forward.__wrapped__(sd, cfg, mel)
+            y[0, 0, t].backward()
+        cols = torch.nonzero(mel.grad[0].abs().amax(dim=0) > 0).reshape(-1)
+        lo.append(f0 - int(cols.min()))
+        hi.append(int(cols.max()) - f0)
+    assert max(lo + hi) == rf, (rf, lo, hi)
+    assert lo[0] == rf and hi[1] == rf  # the first sample of a frame reaches furthest back, the last furthest ahead
