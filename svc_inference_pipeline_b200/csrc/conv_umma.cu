@@ -239,6 +239,7 @@ template <int KS, bool WITH_LO, bool STACKED = false>
 __device__ __forceinline__ int issue_stage(const UmmaParams& p, const int* __restrict__ shifts, int g0, int gtaps, int sh, int nxt_tap,
                                            int min_shift, uint32_t a_stage16, uint32_t b16, uint32_t tmem_acc, uint32_t a_plane16, uint32_t idesc,
                                            uint64_t desc_hi, uint32_t acc0, uint32_t b_tap16, uint32_t col_stride, int mb, uint32_t idesc2 = 0) {
+  const uint32_t corr_col = (uint32_t)p.n_tile;
   for (int g = 0; g < gtaps; ++g) {
     uint32_t a16 = a_stage16 + (uint32_t)(sh - min_shift) * 8u;  // 128 B per row
     sh = shifts[g + 1 < gtaps ? g0 + g + 1 : nxt_tap];
@@ -250,7 +251,11 @@ __device__ __forceinline__ int issue_stage(const UmmaParams& p, const int* __res
         const uint64_t bd = desc_hi | (uint64_t)(b16 + 2u * k);
         if (ptx::elect_one()) ptx::umma_f16(tmem_d, desc_hi | (uint64_t)(a16 + 2u * k), bd, STACKED ? idesc2 : idesc, k == 0 ? first : 1u);
         if (WITH_LO) {
-          if (ptx::elect_one()) ptx::umma_f16(tmem_d, desc_hi | (uint64_t)(a16 + a_plane16 + 2u * k), bd, idesc, 1u);
+          // STACKED: the lo*hi products join the hi*lo ones in the correction columns [n_tile, 2 n_tile), so the main
+          // accumulator takes one addition per K step instead of two.  The tensor core truncates when it adds into an
+          // fp32 accumulator (error ~ steps * 2^-24 * |acc|: measured 3.4e-9 * K relative, tools/conv_precision_diag.py)
+          // and the correction sum is 2^-8 of the main one, so its own truncation does not count.
+          if (ptx::elect_one()) ptx::umma_f16(tmem_d + (STACKED ? corr_col : 0u), desc_hi | (uint64_t)(a16 + a_plane16 + 2u * k), bd, idesc, 1u);
         }
       }
       a16 += (UM_BM * 128u) >> 4;

@@ -154,11 +154,21 @@ int conv_geometry(const bvg_conv_geom* g, bvg_conv_weights* w) {
     } else {
       // fewest tiles of at most 256 columns; a transposed conv keeps each tile inside one phase
       // when the per-phase width allows (then every tile has exactly the taps of its phase)
-      const int cap = (umma_ntile_cap >= 16 && umma_ntile_cap <= 256) ? umma_ntile_cap / 16 * 16 : 256;
-      const int base = (tr && g->cout % 16 == 0) ? g->cout : n_total;
-      const int t = ceil_div(base, cap);
-      n_tile = round_up(ceil_div(base, t), 16);
-      if (tr && g->cout % 16 == 0 && g->cout % n_tile != 0) n_tile = round_up(ceil_div(n_total, ceil_div(n_total, cap)), 16);
+      // split operands, more than one tile's worth of columns (C >= 384: K = Cin x taps in the thousands, where the
+      // tensor core's truncating fp32 accumulation is the largest error of the fp32 path): at most 128 columns, so
+      // that the layer runs "stacked" (below) with the correction products in their own accumulator columns.
+      // Measured on B200 (gpurun_out/r02_ops_fp32_b.txt): C = 768 same speed as 3 x 256, C = 384 9 % faster than 2 x 192;
+      // C = 192 keeps its single 192-column tile (2 x 96 stacked is 8 % slower and K <= 2112 there)
+      const int cap_max = (umma_ntile_cap >= 16 && umma_ntile_cap <= 256) ? umma_ntile_cap / 16 * 16 : 256;
+      int cap = (w->split && umma_stack >= 128 && cap_max > 128 && n_total > 256) ? 128 : cap_max;
+      for (;;) {
+        const int base = (tr && g->cout % 16 == 0) ? g->cout : n_total;
+        const int t = ceil_div(base, cap);
+        n_tile = round_up(ceil_div(base, t), 16);
+        if (tr && g->cout % 16 == 0 && g->cout % n_tile != 0) n_tile = round_up(ceil_div(n_total, ceil_div(n_total, cap)), 16);
+        if (ceil_div(n_total, n_tile) <= BVG_MAX_NTILES || cap == cap_max) break;
+        cap = cap_max;  // a very wide transposed conv (8 x 768 output columns): keep the tile count inside the tap tables
+      }
     }
     BVG_REQUIRE(n_tile % 16 == 0 && n_tile >= 16 && n_tile <= 256, "conv geometry: UMMA n_tile %d must be a multiple of 16 in [16, 256]", n_tile);
   }

@@ -77,8 +77,10 @@ def test_amp_large_argument(ops, golden):
         err = float(np.abs(y - ref64).max())
         print(f"large-argument Activation1d (|a u| ~ 1e2, |y| <= 17): fast_sin={fast} max-abs vs fp64 {err:.3e}; reference fp32 vs fp64 {ref_noise:.3e}")
         # |a*u| reaches ~1e2: fp32 rounding of the product alone moves the phase by ~1e-5
-        assert err < 3e-4, (fast, err)
-        assert np.abs(y - g["big_y"]).max() < 3e-4
+        # measured on B200: 4.9e-5 with MUFU on the raw argument, 5.0e-5 with the exact reduction (3x the reference's
+        # own fp32 noise on this input, the same for both: the raw-argument cosine costs no accuracy)
+        assert err < 1e-4, (fast, err)
+        assert np.abs(y - g["big_y"]).max() < 1e-4
 
 
 @pytest.mark.parametrize("shape", [(2, 24, 1000), (1, 768, 301), (3, 6, 97), (2, 5, 64), (1, 48, 2500)])
