@@ -378,7 +378,11 @@ def main():
                         "amp_frac": AMP_ELEMS_PER_FRAME * frames * 4 / (bprof["amp_ms"] / 1e3) / 1e9 / peaks["hbm"],
                         "class_ms_per_step": {k: bprof[k] for k in ("conv_ms", "amp_ms", "other_ms", "total_ms")}}
         if gold is not None:
-            line["parity"].update({"bf16_path_snr_db": snr_db(gold["y_f64"], yb[7:8].cpu().numpy()), "gate_bf16_snr_db": 35.0})
+            from svc_inference_pipeline_b200.utils.mel import log_mel_l1  # the reference's analysis (utils/mel.py:130-174) on the device
+
+            ref_dev = torch.from_numpy(gold["y_f64"].astype(np.float32)).to(dev)
+            line["parity"].update({"bf16_path_snr_db": snr_db(gold["y_f64"], yb[7:8].cpu().numpy()), "gate_bf16_snr_db": 35.0,
+                                   "bf16_path_log_mel_l1": log_mel_l1(ref_dev, yb[7:8]), "gate_bf16_log_mel_l1": 1e-2})
         model.set_precision(args.precision)
 
     if rank == 0:

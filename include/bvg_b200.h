@@ -12,6 +12,8 @@
  *  - plain C types only; every pointer named d_* is a DEVICE pointer borrowed from the caller
  *    (torch owns all memory; the library never allocates device memory);
  *  - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *  - no process-global mutable state: test / tuning knobs are a struct the caller attaches to a descriptor
+ *    (bvg_tuning); the only caches are keyed by (device, kernel) and guarded by a mutex;
  *  - every function returns 0 on success, a negative BVG_E* code otherwise, and never throws;
  *    bvg_last_error() returns a thread-local human-readable message for the last failure;
  *  - activations are CHANNELS-LAST inside the library: [B, L, C] with C contiguous
@@ -31,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BVG_ABI_VERSION 3  /* 2: bvg_conv_geom.fold, bvg_conv_desc.pre_amp; 3: bvg_stitch_fwd */
+#define BVG_ABI_VERSION 4  /* 2: bvg_conv_geom.fold, bvg_conv_desc.pre_amp; 3: bvg_stitch_fwd; 4: bvg_tuning in the descriptors (bvg_set_tuning removed), bvg_logmel_fwd */
 
 enum bvg_status {
   BVG_OK = 0,
@@ -47,6 +49,30 @@ enum bvg_backend {
   BVG_SIMT = 0, /* fp32 FFMA implicit GEMM on CUDA cores: exact-fp32 anchor path */
   BVG_UMMA = 1  /* tcgen05.mma + TMEM accumulators fed by TMA (bf16 operands, fp32 accumulate) */
 };
+
+/* Test / A-B knobs.  They travel WITH the descriptor they apply to (bvg_amp_desc.tune, bvg_conv_desc.tune,
+ * bvg_conv_geom.tune; NULL = the library's own choices), so the library keeps no process-global mutable state
+ * and two threads can run differently tuned calls side by side.  Fill with bvg_tuning_defaults() first. */
+typedef struct bvg_tuning {
+  int32_t amp_vec;         /* 0 = choose; else force channels per thread of the FFMA Activation1d kernel (1, 2, 4) */
+  int32_t amp_chunk;       /* 0 = choose; else 12-step block pairs per thread */
+  int32_t amp_mma;         /* default 1: tensor-core Activation1d for BF16 -> BF16; 2: also F32 -> SPLIT; 0: never */
+  int32_t amp_mma_tiles;   /* 0 = choose; time tiles per CTA of the tensor-core Activation1d */
+  int32_t amp_packed;      /* default 1: FFMA2 kernel for two channels per thread; 0: scalar FFMA */
+  int32_t amp_stream;      /* default 0: per-warp streaming tensor-core Activation1d (F32 -> SPLIT) */
+  int32_t amp_stream_bf16; /* default 0: the same for BF16 -> BF16 */
+  int32_t amp_ct;          /* default 1: per-channel-count instantiations of the FFMA2 kernel */
+  int32_t umma_mb;         /* 0 = choose; force M blocks per tile */
+  int32_t umma_wide_mb2;   /* 0 = SPLIT only; 1 = every tile that fits; -1 = never: two row blocks on one TMEM stage */
+  int32_t umma_max_ctas;   /* 0 = all SMs; cap of the persistent grid */
+  int32_t umma_ntile_cap;  /* default 256: widest N tile bvg_conv_geometry chooses */
+  int32_t umma_tap_group;  /* 0 = choose; taps per weight stage */
+  int32_t umma_a_stages;   /* 0 = choose; activation stages (2..4) */
+  int32_t umma_stack;      /* default 128: widest n_tile with stacked (hi, lo) weight planes (0 = never) */
+  int32_t _reserved;
+} bvg_tuning;
+
+void bvg_tuning_defaults(bvg_tuning* t);
 
 /* A tensor handed to a kernel: base pointer(s) + element format.  `lo` is only read for SPLIT. */
 typedef struct bvg_tensor {
@@ -73,7 +99,10 @@ typedef struct bvg_amp_desc {
   float taps_up[12];   /* upsample.filter   (state_dict buffer, modules/bigvgan.py:273-276) */
   float taps_down[12]; /* downsample.lowpass.filter (modules/bigvgan.py:220-221) */
   int32_t B, L, C;
-  int32_t fast_sin;    /* 1: MUFU sin (bf16 path); 0: range-reduced polynomial (fp32 path) */
+  int32_t fast_sin;    /* 1: MUFU.COS / MUFU.SIN on the raw argument 2 a u (default of both paths: measured equal to the
+                          reduced form on every golden, tests/test_gpu_ops.py::test_amp_large_argument); 0: the argument is
+                          first reduced exactly to [-1/2, 1/2] turns (Generator(precise_sin=True)) */
+  const bvg_tuning* tune; /* NULL = defaults */
 } bvg_amp_desc;
 
 int bvg_amp_fwd(const bvg_amp_desc* d, void* stream);
@@ -123,6 +152,7 @@ typedef struct bvg_conv_desc {
                                          the kernel computes its operand from pre_amp->x (F32 [B, L, Cin]) and x above is
                                          ignored; pre_amp->y is not written.  The AMP-into-conv fusion of the narrow stages:
                                          modules/bigvgan.py:428-431  xt = c1(a1(x)); xt = c2(a2(xt)) */
+  const bvg_tuning* tune; /* NULL = defaults */
 } bvg_conv_desc;
 
 int bvg_conv_fwd(const bvg_conv_desc* d, void* stream);
@@ -148,6 +178,8 @@ typedef struct bvg_conv_geom {
                           arrangement of the original ones (row p_out of a block of outputs takes original tap j from
                           input row P*shift + p_in with j*d - padding = P*shift + p_in - p_out).  The caller passes
                           L/P as bvg_conv_desc.L; w->cin, n_total, x_pitch describe the folded layer. */
+  int32_t _pad;
+  const bvg_tuning* tune; /* NULL = defaults (umma_ntile_cap, umma_stack) */
 } bvg_conv_geom;
 
 int bvg_conv_pack_bytes(const bvg_conv_geom* g, size_t* weight_plane_bytes, size_t* bias_bytes);
@@ -237,6 +269,28 @@ typedef struct bvg_stitch_desc {
 
 int bvg_stitch_fwd(const bvg_stitch_desc* d, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Log-mel front end (replaces mel_spectrogram, utils/mel.py:130-174, which the
+ * reference runs with torch.stft + a librosa mel basis on the host: reflect pad (n_fft - hop) / 2, frames
+ * every hop with center = False, periodic hann window of `win` samples, sqrt(re^2 + im^2 + 1e-9), basis
+ * matmul, log(max(., clip))).
+ *   d_wave : float [B, n] (row stride wave_stride);   d_out : float [B, n_mels, frames],
+ *   frames = 1 + (n + 2 * ((n_fft - hop) / 2) - n_fft) / hop  (checked);
+ *   d_basis: float [n_mels, n_fft / 2 + 1], the caller's mel basis (librosa.filters.mel for the reference);
+ *   d_band : int32 [n_mels][2] = first and one-past-last non-zero bin of every band.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct bvg_logmel_desc {
+  const float* d_wave;
+  int64_t wave_stride;
+  float* d_out;
+  const float* d_basis;
+  const int32_t* d_band;
+  int32_t B, n, n_fft, hop, win, n_mels, frames;
+  float clip; /* 1e-5 in the reference (dynamic_range_compression_torch, utils/mel.py:25-26) */
+} bvg_logmel_desc;
+
+int bvg_logmel_fwd(const bvg_logmel_desc* d, void* stream);
+
 /* Layout/format helpers used by tests and by the sharded stitch. */
 int bvg_convert(const bvg_tensor* src, const bvg_tensor* dst, size_t n_elems, void* stream);
 
@@ -276,7 +330,6 @@ void bvg_program_destroy(bvg_program* p);
 int bvg_abi_version(void);
 const char* bvg_last_error(void);
 int bvg_device_check(int device); /* BVG_OK iff `device` is compute capability 10.x */
-int bvg_set_tuning(const char* name, int value); /* test / tuning knobs: amp_vec, amp_chunk, amp_mma, amp_mma_tiles, amp_packed, amp_stream, amp_stream_bf16, amp_ct, umma_mb, umma_wide_mb2, umma_max_ctas, umma_ntile_cap, umma_tap_group, umma_a_stages, umma_stack */
 size_t bvg_sizeof_op(void);       /* ABI self-check for the ctypes mirror */
 size_t bvg_sizeof_conv_weights(void);
 

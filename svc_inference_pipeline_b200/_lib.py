@@ -16,11 +16,19 @@ F32, BF16, SPLIT = 0, 1, 2
 SIMT, UMMA = 0, 1
 OP_PACK, OP_AMP, OP_CONV, OP_POST = 0, 1, 2, 3
 MAX_TAPS, MAX_NTILES = 16, 32
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class BvgError(RuntimeError):
     pass
+
+
+class Tuning(C.Structure):
+    """``bvg_tuning``: test / A-B knobs attached to a descriptor (``tune`` field; NULL = the library's defaults)."""
+
+    _fields_ = [(n, C.c_int32) for n in (
+        "amp_vec", "amp_chunk", "amp_mma", "amp_mma_tiles", "amp_packed", "amp_stream", "amp_stream_bf16", "amp_ct",
+        "umma_mb", "umma_wide_mb2", "umma_max_ctas", "umma_ntile_cap", "umma_tap_group", "umma_a_stages", "umma_stack", "_reserved")]
 
 
 class Tensor(C.Structure):
@@ -39,6 +47,7 @@ class AmpDesc(C.Structure):
         ("L", C.c_int32),
         ("C", C.c_int32),
         ("fast_sin", C.c_int32),
+        ("tune", C.POINTER(Tuning)),
     ]
 
 
@@ -72,6 +81,7 @@ class ConvDesc(C.Structure):
         ("L", C.c_int32),
         ("w", C.POINTER(ConvWeights)),
         ("pre_amp", C.c_void_p),  # const bvg_amp_desc*: Activation1d fused in front of the convolution (or NULL)
+        ("tune", C.POINTER(Tuning)),
     ]
 
 
@@ -88,6 +98,8 @@ class ConvGeom(C.Structure):
         ("split", C.c_int32),
         ("n_tile", C.c_int32),
         ("fold", C.c_int32),
+        ("_pad", C.c_int32),
+        ("tune", C.POINTER(Tuning)),
     ]
 
 
@@ -144,6 +156,24 @@ class StitchDesc(C.Structure):
     ]
 
 
+class LogmelDesc(C.Structure):
+    _fields_ = [
+        ("d_wave", C.c_void_p),
+        ("wave_stride", C.c_int64),
+        ("d_out", C.c_void_p),
+        ("d_basis", C.c_void_p),
+        ("d_band", C.c_void_p),
+        ("B", C.c_int32),
+        ("n", C.c_int32),
+        ("n_fft", C.c_int32),
+        ("hop", C.c_int32),
+        ("win", C.c_int32),
+        ("n_mels", C.c_int32),
+        ("frames", C.c_int32),
+        ("clip", C.c_float),
+    ]
+
+
 class _OpUnion(C.Union):
     _fields_ = [("pack", PackDesc), ("amp", AmpDesc), ("conv", ConvDesc), ("post", PostDesc)]
 
@@ -171,12 +201,13 @@ EXPORTS = [
     "bvg_pack_mel",
     "bvg_tail_fwd",
     "bvg_stitch_fwd",
+    "bvg_logmel_fwd",
     "bvg_convert",
     "bvg_program_create",
     "bvg_program_run",
     "bvg_program_run_interleaved",
     "bvg_program_run_timed",
-    "bvg_set_tuning",
+    "bvg_tuning_defaults",
     "bvg_program_num_launches",
     "bvg_program_destroy",
 ]
@@ -199,13 +230,14 @@ def lib():
     L.bvg_abi_version.restype = C.c_int
     for name, argtypes in {
         "bvg_device_check": [C.c_int],
-        "bvg_set_tuning": [C.c_char_p, C.c_int],
+        "bvg_tuning_defaults": [C.POINTER(Tuning)],
         "bvg_amp_fwd": [C.POINTER(AmpDesc), C.c_void_p],
         "bvg_conv_fwd": [C.POINTER(ConvDesc), C.c_void_p],
         "bvg_post_fwd": [C.POINTER(PostDesc), C.c_void_p],
         "bvg_pack_mel": [C.POINTER(PackDesc), C.c_void_p],
         "bvg_tail_fwd": [C.POINTER(TailDesc), C.c_void_p],
         "bvg_stitch_fwd": [C.POINTER(StitchDesc), C.c_void_p],
+        "bvg_logmel_fwd": [C.POINTER(LogmelDesc), C.c_void_p],
         "bvg_convert": [C.POINTER(Tensor), C.POINTER(Tensor), C.c_size_t, C.c_void_p],
         "bvg_conv_geometry": [C.POINTER(ConvGeom), C.POINTER(ConvWeights)],
         "bvg_conv_pack_bytes": [C.POINTER(ConvGeom), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)],
@@ -220,7 +252,7 @@ def lib():
     }.items():
         fn = getattr(L, name)
         fn.argtypes = argtypes
-        fn.restype = None if name == "bvg_program_destroy" else C.c_int
+        fn.restype = None if name in ("bvg_program_destroy", "bvg_tuning_defaults") else C.c_int
     if L.bvg_abi_version() != ABI_VERSION:
         raise BvgError(f"ABI mismatch: library reports version {L.bvg_abi_version()}, binding expects {ABI_VERSION}")
     if L.bvg_sizeof_op() != C.sizeof(Op) or L.bvg_sizeof_conv_weights() != C.sizeof(ConvWeights):
@@ -249,5 +281,39 @@ def require_sm100(device_index: int) -> None:
         _checked_devices.add(device_index)
 
 
+# ---- test / A-B knobs -----------------------------------------------------------------------------------
+# The library has no global knobs: a ``bvg_tuning`` travels with each descriptor.  For tests and the A/B tools the
+# BINDING keeps one process-wide ``Tuning`` object that the descriptor builders (ops.py, modules/bigvgan.py) attach
+# when any field differs from the defaults; programs deep-copy it at creation.
+_tuning = None
+_tuning_defaults = None
+
+
+def _tuning_state():
+    global _tuning, _tuning_defaults
+    if _tuning is None:
+        _tuning, _tuning_defaults = Tuning(), Tuning()
+        lib().bvg_tuning_defaults(C.byref(_tuning))
+        lib().bvg_tuning_defaults(C.byref(_tuning_defaults))
+    return _tuning, _tuning_defaults
+
+
 def set_tuning(name: str, value: int) -> None:
-    check(lib().bvg_set_tuning(name.encode(), int(value)), f"set_tuning({name})")
+    """Set one knob of the binding's ``Tuning`` object (applies to descriptors built afterwards)."""
+    t, _ = _tuning_state()
+    if name not in dict(Tuning._fields_) or name.startswith("_"):
+        raise BvgError(f"unknown tuning knob '{name}'")
+    setattr(t, name, int(value))
+
+
+def reset_tuning() -> None:
+    t, _ = _tuning_state()
+    lib().bvg_tuning_defaults(C.byref(t))
+
+
+def tuning_ptr():
+    """Pointer to the binding's ``Tuning`` for a descriptor's ``tune`` field, or NULL when every knob is at its default."""
+    t, d = _tuning_state()
+    if bytes(t) == bytes(d):
+        return None
+    return C.pointer(t)

@@ -387,7 +387,6 @@ __global__ void __launch_bounds__(128, 6) amp_kernel_p2(const __grid_constant__ 
   }
 }
 
-int amp_packed_enable = 1;  // test/tuning hook ("amp_packed"): 0 = scalar FFMA kernel for two channels per thread too
 
 template <bool IN_BF16, int OUT_MODE, bool FAST_SIN, int CT>
 static cudaError_t launch_amp_p2_ct(const AmpParams& p, cudaStream_t st) {
@@ -401,12 +400,11 @@ static cudaError_t launch_amp_p2_ct(const AmpParams& p, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-int amp_ct_enable = 1;  // tuning hook ("amp_ct"): 0 = runtime channel count for every shape
 
 // the generator's own operand format (F32 -> SPLIT) gets one instantiation per channel count of the
 // repo / v2 generators; everything else runs with the channel count as a kernel parameter
 template <bool IN_BF16, int OUT_MODE, bool FAST_SIN>
-static cudaError_t launch_amp_p2_sin(const AmpParams& p, cudaStream_t st) {
+static cudaError_t launch_amp_p2_sin(const AmpParams& p, cudaStream_t st, bool amp_ct_enable) {
   if constexpr (!IN_BF16 && OUT_MODE == BVG_SPLIT) {
     if (amp_ct_enable) switch (p.C) {
       case 24: return launch_amp_p2_ct<IN_BF16, OUT_MODE, FAST_SIN, 24>(p, st);
@@ -422,19 +420,19 @@ static cudaError_t launch_amp_p2_sin(const AmpParams& p, cudaStream_t st) {
 }
 
 template <bool IN_BF16, int OUT_MODE>
-static cudaError_t launch_amp_p2(const AmpParams& p, bool fast, cudaStream_t st) {
-  return fast ? launch_amp_p2_sin<IN_BF16, OUT_MODE, true>(p, st) : launch_amp_p2_sin<IN_BF16, OUT_MODE, false>(p, st);
+static cudaError_t launch_amp_p2(const AmpParams& p, bool fast, cudaStream_t st, bool ct) {
+  return fast ? launch_amp_p2_sin<IN_BF16, OUT_MODE, true>(p, st, ct) : launch_amp_p2_sin<IN_BF16, OUT_MODE, false>(p, st, ct);
 }
 
-static cudaError_t launch_amp_packed(const AmpParams& p, bool in_bf16, int out_mode, bool fast, cudaStream_t st) {
+static cudaError_t launch_amp_packed(const AmpParams& p, bool in_bf16, int out_mode, bool fast, cudaStream_t st, bool ct) {
   if (in_bf16) {
-    if (out_mode == BVG_F32) return launch_amp_p2<true, BVG_F32>(p, fast, st);
-    if (out_mode == BVG_BF16) return launch_amp_p2<true, BVG_BF16>(p, fast, st);
-    return launch_amp_p2<true, BVG_SPLIT>(p, fast, st);
+    if (out_mode == BVG_F32) return launch_amp_p2<true, BVG_F32>(p, fast, st, ct);
+    if (out_mode == BVG_BF16) return launch_amp_p2<true, BVG_BF16>(p, fast, st, ct);
+    return launch_amp_p2<true, BVG_SPLIT>(p, fast, st, ct);
   }
-  if (out_mode == BVG_F32) return launch_amp_p2<false, BVG_F32>(p, fast, st);
-  if (out_mode == BVG_BF16) return launch_amp_p2<false, BVG_BF16>(p, fast, st);
-  return launch_amp_p2<false, BVG_SPLIT>(p, fast, st);
+  if (out_mode == BVG_F32) return launch_amp_p2<false, BVG_F32>(p, fast, st, ct);
+  if (out_mode == BVG_BF16) return launch_amp_p2<false, BVG_BF16>(p, fast, st, ct);
+  return launch_amp_p2<false, BVG_SPLIT>(p, fast, st, ct);
 }
 
 template <bool IN_BF16, int OUT_MODE, int VEC, bool FAST_SIN>
@@ -467,8 +465,6 @@ int amp_mma_forward(const bvg_amp_desc* d, cudaStream_t st);
 bool amp_stream_supported(const bvg_amp_desc* d);            // amp_stream.cu: per-warp streaming variant (F32 -> SPLIT)
 int amp_stream_forward(const bvg_amp_desc* d, cudaStream_t st);
 
-int amp_vec_override = 0;  // test/tuning hook: force VEC (set through bvg_set_tuning)
-int amp_chunk_override = 0;
 
 int amp_forward(const bvg_amp_desc* d, cudaStream_t st) {
   BVG_REQUIRE(d != nullptr, "amp: null descriptor");
@@ -481,13 +477,14 @@ int amp_forward(const bvg_amp_desc* d, cudaStream_t st) {
 
   // the two operand formats of the generator (F32 -> SPLIT, BF16 -> BF16) run the FIRs on the
   // tensor cores; every other combination stays on the FFMA kernel below
+  const bvg_tuning T = tune_of(d->tune);
   if (amp_stream_supported(d)) return amp_stream_forward(d, st);
   if (amp_mma_supported(d)) return amp_mma_forward(d, st);
 
   // two channels per thread: measured 15-25 % faster than four on B200 (64 vs 164 registers ->
   // 2.7x the resident warps; profiles/r01_amp_sweep.txt)
   int vec = (d->C % 2 == 0) ? 2 : 1;
-  if (amp_vec_override && d->C % amp_vec_override == 0) vec = amp_vec_override;
+  if (T.amp_vec && d->C % T.amp_vec == 0) vec = T.amp_vec;
 
   AmpParams p;
   p.x = d->x.d_ptr;
@@ -510,7 +507,7 @@ int amp_forward(const bvg_amp_desc* d, cudaStream_t st) {
   int nblk2 = 8;
   const long long want = 148ll * 512 * 3;
   while (nblk2 > 1 && (long long)d->B * p.CG * ceil_div(d->L, 12 * nblk2) < want) nblk2 >>= 1;
-  if (amp_chunk_override > 0) nblk2 = amp_chunk_override;
+  if (T.amp_chunk > 0) nblk2 = T.amp_chunk;
   p.nblk2 = nblk2;
   p.nchunks = ceil_div(d->L, 12 * nblk2);
   p.total_threads = (long long)d->B * p.nchunks * p.CG;
@@ -520,8 +517,8 @@ int amp_forward(const bvg_amp_desc* d, cudaStream_t st) {
   const bool in_bf16 = d->x.dtype == BVG_BF16;
   if (vec == 4)
     e = launch_amp_vec<4>(p, in_bf16, d->y.dtype, d->fast_sin != 0, st);
-  else if (vec == 2 && amp_packed_enable)
-    e = launch_amp_packed(p, in_bf16, d->y.dtype, d->fast_sin != 0, st);
+  else if (vec == 2 && T.amp_packed)
+    e = launch_amp_packed(p, in_bf16, d->y.dtype, d->fast_sin != 0, st, T.amp_ct != 0);
   else if (vec == 2)
     e = launch_amp_vec<2>(p, in_bf16, d->y.dtype, d->fast_sin != 0, st);
   else

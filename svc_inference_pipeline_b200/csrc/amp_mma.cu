@@ -365,14 +365,14 @@ static cudaError_t launch_amp_mma_ng(const AmpMmaParams& p, int ng, cudaStream_t
   return launch_amp_mma<IN_BF16, OUT_MODE, FAST_SIN, 2>(p, st);
 }
 
-int amp_mma_tiles = 0;   // test/tuning hook ("amp_mma_tiles"): time tiles per CTA, 0 = choose
-// test/tuning hook (bvg_set_tuning "amp_mma"): 0 = never, 1 = where it measured faster than the FFMA2
-// kernel on B200 (profiles/r01_ncu_summary_v7.md section 4: BF16 -> BF16, every C that is a multiple of 8), 2 = wherever it is supported
-int amp_mma_enable = 1;
+// bvg_tuning.amp_mma: 0 = never, 1 (default) = where it measured faster than the FFMA2 kernel on B200
+// (profiles/r01_ncu_summary_v7.md section 4: BF16 -> BF16, every C that is a multiple of 8), 2 = wherever it is supported;
+// bvg_tuning.amp_mma_tiles: time tiles per CTA, 0 = choose
 
 // The tensor-core kernel takes F32 -> SPLIT (fp32 path) and BF16 -> BF16 (bf16 path) with C a multiple
 // of 8.  Everything else stays on amp_kernel.cu.
 bool amp_mma_supported(const bvg_amp_desc* d) {
+  const int amp_mma_enable = tune_of(d->tune).amp_mma;
   if (!amp_mma_enable) return false;
   if (d->C % 8 != 0) return false;
   const bool f32_split = d->x.dtype == BVG_F32 && d->y.dtype == BVG_SPLIT;
@@ -411,6 +411,7 @@ int amp_mma_forward(const bvg_amp_desc* d, cudaStream_t st) {
   p.n_tiles = ceil_div(p.m_last + 2, AM_NB);
   // tiles per CTA: long walks amortise the per-CTA set-up (Toeplitz fragments, warm-up block) while
   // the grid still covers every SM with a few rounds of co-resident CTAs
+  const int amp_mma_tiles = tune_of(d->tune).amp_mma_tiles;
   int tpc = amp_mma_tiles > 0 ? amp_mma_tiles : 32;
   while (tpc > 1 && (long long)d->B * p.n_cg * ceil_div(p.n_tiles, tpc) < 148ll * 5 * 3) tpc >>= 1;
   p.tiles_per_cta = tpc;

@@ -264,22 +264,20 @@ __global__ void __launch_bounds__(32 * RS_WARPS) amp_stream_kernel(const __grid_
   asm volatile("cp.async.wait_group 0;" ::: "memory");  // nothing may be in flight into shared memory at exit
 }
 
-extern int amp_mma_tiles;
-// test/tuning hook ("amp_stream"): 1 = F32 -> SPLIT runs here.  Off by default: measured on B200 (in-program, fp32
+// bvg_tuning.amp_stream: 1 = F32 -> SPLIT runs here.  Off by default: measured on B200 (in-program, fp32
 // path) 3.0-3.2 TB/s against 3.5-3.6 TB/s for the FFMA2 kernel -- ncu: 46 thread-instructions per element, a third of
 // them the bf16 (hi, lo) splitting of x, s and z that the fp32 path's 16-bit operands need, so the tensor-core
 // formulation does not pay here the way it does on the bf16 path (amp_mma.cu, fp16 single-term s).
-int amp_stream_enable = 0;
 
-// "amp_stream_bf16": BF16 -> BF16 on the streaming kernel (1) or on the staged amp_mma kernel (0, default: the
+// bvg_tuning.amp_stream_bf16: BF16 -> BF16 on the streaming kernel (1) or on the staged amp_mma kernel (0, default: the
 // staged kernel is level for C >= 48 and 15 % ahead for C = 24, gpurun_out/ab_streambf16.txt)
-int amp_stream_bf16_enable = 0;
 
 bool amp_stream_supported(const bvg_amp_desc* d) {
   if (d->C % 8 != 0) return false;
   const bool f32_split = d->x.dtype == BVG_F32 && d->y.dtype == BVG_SPLIT;
   const bool bf_bf = d->x.dtype == BVG_BF16 && d->y.dtype == BVG_BF16;
-  if (!((f32_split && amp_stream_enable) || (bf_bf && amp_stream_bf16_enable))) return false;
+  const bvg_tuning T = tune_of(d->tune);
+  if (!((f32_split && T.amp_stream) || (bf_bf && T.amp_stream_bf16))) return false;
   if (((uintptr_t)d->x.d_ptr & 15) || ((uintptr_t)d->y.d_ptr & 15) || (f32_split && ((uintptr_t)d->y.d_lo & 15))) return false;
   return true;
 }
@@ -301,6 +299,7 @@ int amp_stream_forward(const bvg_amp_desc* d, cudaStream_t st) {
   p.n_cg = ceil_div(d->C, 16 * RS_WARPS);
   p.m_last = d->L >= 4 ? (d->L - 4) / 8 : -1;
   p.n_tiles = ceil_div(p.m_last + 2, AM_NB);
+  const int amp_mma_tiles = tune_of(d->tune).amp_mma_tiles;
   int tpc = amp_mma_tiles > 0 ? amp_mma_tiles : 32;
   while (tpc > 1 && (long long)d->B * p.n_cg * ceil_div(p.n_tiles, tpc) < 148ll * 5 * 3) tpc >>= 1;
   p.tiles_per_cta = tpc;

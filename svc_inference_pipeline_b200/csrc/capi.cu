@@ -42,6 +42,7 @@ int post_forward(const bvg_post_desc* d, cudaStream_t st);
 int pack_mel(const bvg_pack_desc* d, cudaStream_t st);
 int tail_forward(const bvg_tail_desc* d, cudaStream_t st);
 int stitch_forward(const bvg_stitch_desc* d, cudaStream_t st);
+int logmel_forward(const bvg_logmel_desc* d, cudaStream_t st);
 int convert(const bvg_tensor* src, const bvg_tensor* dst, size_t n, cudaStream_t st);
 int conv_geometry(const bvg_conv_geom* g, bvg_conv_weights* w);
 size_t conv_plane_elems(const bvg_conv_weights* w);
@@ -53,7 +54,6 @@ struct UmmaLaunch;
 int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out);
 int conv_umma_launch(const UmmaLaunch* l, cudaStream_t st);
 size_t umma_launch_size();
-extern int amp_vec_override, amp_chunk_override, umma_mb, umma_wide_mb2, umma_max_ctas, umma_ntile_cap, umma_tap_group, umma_a_stages, umma_stack, amp_mma_enable, amp_mma_tiles, amp_packed_enable, amp_stream_enable, amp_stream_bf16_enable, amp_ct_enable;
 
 static int conv_forward(const bvg_conv_desc* d, cudaStream_t st) {
   BVG_REQUIRE(d && d->w, "conv: null descriptor");
@@ -71,10 +71,12 @@ static int conv_forward(const bvg_conv_desc* d, cudaStream_t st) {
 struct bvg_program {
   std::vector<bvg_op> ops;
   std::vector<bvg_conv_weights*> owned_weights;
+  std::vector<bvg_tuning*> owned_tunings;   // deep copies of the descriptors' bvg_tuning (the caller's may go away)
   std::vector<void*> umma;  // UmmaLaunch* per op (nullptr for the others)
   int launches = 0;
   ~bvg_program() {
     for (auto* w : owned_weights) delete w;
+    for (auto* t : owned_tunings) delete t;
     for (auto* u : umma) ::operator delete(u);
   }
 };
@@ -98,28 +100,8 @@ int bvg_device_check(int device) {
   return BVG_OK;
 }
 
-int bvg_set_tuning(const char* name, int value) {
-  if (!name) return BVG_EINVAL;
-  if (!strcmp(name, "amp_vec")) bvg::amp_vec_override = value;
-  else if (!strcmp(name, "amp_chunk")) bvg::amp_chunk_override = value;
-  else if (!strcmp(name, "umma_mb")) bvg::umma_mb = value;
-  else if (!strcmp(name, "umma_wide_mb2")) bvg::umma_wide_mb2 = value;
-  else if (!strcmp(name, "umma_max_ctas")) bvg::umma_max_ctas = value;
-  else if (!strcmp(name, "umma_ntile_cap")) bvg::umma_ntile_cap = value;
-  else if (!strcmp(name, "umma_tap_group")) bvg::umma_tap_group = value;
-  else if (!strcmp(name, "umma_a_stages")) bvg::umma_a_stages = value;
-  else if (!strcmp(name, "umma_stack")) bvg::umma_stack = value;
-  else if (!strcmp(name, "amp_mma")) bvg::amp_mma_enable = value;
-  else if (!strcmp(name, "amp_mma_tiles")) bvg::amp_mma_tiles = value;
-  else if (!strcmp(name, "amp_packed")) bvg::amp_packed_enable = value;
-  else if (!strcmp(name, "amp_stream")) bvg::amp_stream_enable = value;
-  else if (!strcmp(name, "amp_stream_bf16")) bvg::amp_stream_bf16_enable = value;
-  else if (!strcmp(name, "amp_ct")) bvg::amp_ct_enable = value;
-  else {
-    bvg::set_error("unknown tuning knob '%s'", name);
-    return BVG_EINVAL;
-  }
-  return BVG_OK;
+void bvg_tuning_defaults(bvg_tuning* t) {
+  if (t) *t = bvg::default_tuning();
 }
 
 int bvg_amp_fwd(const bvg_amp_desc* d, void* stream) { return bvg::amp_forward(d, (cudaStream_t)stream); }
@@ -127,6 +109,7 @@ int bvg_conv_fwd(const bvg_conv_desc* d, void* stream) { return bvg::conv_forwar
 int bvg_post_fwd(const bvg_post_desc* d, void* stream) { return bvg::post_forward(d, (cudaStream_t)stream); }
 int bvg_pack_mel(const bvg_pack_desc* d, void* stream) { return bvg::pack_mel(d, (cudaStream_t)stream); }
 int bvg_tail_fwd(const bvg_tail_desc* d, void* stream) { return bvg::tail_forward(d, (cudaStream_t)stream); }
+int bvg_logmel_fwd(const bvg_logmel_desc* d, void* stream) { return bvg::logmel_forward(d, (cudaStream_t)stream); }
 int bvg_stitch_fwd(const bvg_stitch_desc* d, void* stream) { return bvg::stitch_forward(d, (cudaStream_t)stream); }
 int bvg_convert(const bvg_tensor* src, const bvg_tensor* dst, size_t n, void* stream) {
   return bvg::convert(src, dst, n, (cudaStream_t)stream);
@@ -169,6 +152,14 @@ int bvg_program_create(const bvg_op* ops, int32_t n_ops, bvg_program** out) {
   p->umma.assign(n_ops, nullptr);
   for (int i = 0; i < n_ops; ++i) {
     bvg_op& op = p->ops[i];
+    if (op.kind == BVG_OP_AMP && op.u.amp.tune) {
+      p->owned_tunings.push_back(new bvg_tuning(*op.u.amp.tune));
+      op.u.amp.tune = p->owned_tunings.back();
+    }
+    if (op.kind == BVG_OP_CONV && op.u.conv.tune) {
+      p->owned_tunings.push_back(new bvg_tuning(*op.u.conv.tune));
+      op.u.conv.tune = p->owned_tunings.back();
+    }
     if (op.kind == BVG_OP_CONV) {
       if (!op.u.conv.w) {
         bvg::set_error("program_create: op %d has no weights", i);

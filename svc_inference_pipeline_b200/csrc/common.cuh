@@ -34,6 +34,18 @@ int cuda_fail(cudaError_t e, const char* what);
 // preference) are per device, so a process that drives several GPUs must set them on each.  Thread-safe.
 bool first_use_on_device(const void* kernel);
 
+// the knobs of a call: the caller's bvg_tuning or the defaults
+inline bvg_tuning default_tuning() {
+  bvg_tuning t = {};
+  t.amp_mma = 1;
+  t.amp_packed = 1;
+  t.amp_ct = 1;
+  t.umma_ntile_cap = 256;
+  t.umma_stack = 128;
+  return t;
+}
+inline bvg_tuning tune_of(const bvg_tuning* t) { return t ? *t : default_tuning(); }
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 

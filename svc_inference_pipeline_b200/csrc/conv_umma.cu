@@ -866,22 +866,18 @@ struct UmmaLaunch {
   size_t smem;
 };
 
-int umma_mb = 0;         // tuning/test hook: force M blocks per tile (0 = choose)
-// mb = 2 with a single TMEM stage (2 x 256 columns): 0 = for SPLIT operands only (three MMA passes make a tile
-// three times longer, so the un-overlapped epilogue costs ~1 % while every weight box feeds two row blocks:
+// bvg_tuning knobs read here (bvg_conv_desc.tune): umma_mb (force M blocks per tile), umma_max_ctas (cap the persistent
+// grid), umma_tap_group (taps per weight stage), umma_a_stages (activation stages), and
+// umma_wide_mb2 -- mb = 2 with a single TMEM stage (2 x 256 columns): 0 = for SPLIT operands only (three MMA passes make a
+// tile three times longer, so the un-overlapped epilogue costs ~1 % while every weight box feeds two row blocks:
 // stage-0 convolutions 19.2 -> 17.9 ms per forward, gpurun_out/ab_mb2_fp32.txt; bf16 operands lose 13 %),
 // 1 = for every tile that fits (also 192 columns), -1 = never
-int umma_wide_mb2 = 0;
-int umma_max_ctas = 0;   // tuning/test hook: cap the persistent grid
-int umma_tap_group = 0;  // tuning/test hook: taps per weight stage (0 = choose)
-int umma_a_stages = 0;   // tuning/test hook: activation stages (0 = choose)
-
 static const int kBarBytes = 8 * (2 * UM_MAX_A_STAGES + 2 * UM_MAX_B_STAGES + 2 * UM_MAX_T_STAGES) + 16;
 
 // shared-memory plan for a given number of M blocks: picks the taps per weight stage (narrow N
 // tiles group several taps into one TMA box / one barrier round trip) and returns the number of
 // weight stages that fit
-static int plan_smem(int mb, int a_stages, int max_span, int planes, int n_tile, int max_taps, int* box_rows, int* boxes, int* tap_group) {
+static int plan_smem(int umma_tap_group, int mb, int a_stages, int max_span, int planes, int n_tile, int max_taps, int* box_rows, int* boxes, int* tap_group) {
   const int rows = mb * UM_BM + max_span;
   const int nb = (rows + 255) / 256;
   const int br = (((rows + nb - 1) / nb) + 7) / 8 * 8;
@@ -927,6 +923,9 @@ int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out) {
   BVG_REQUIRE(w->x_pitch % 8 == 0, "conv_umma: channel pitch %d must be a multiple of 8 (16-byte TMA strides)", w->x_pitch);
   BVG_REQUIRE((fused || ((uintptr_t)d->x.d_ptr & 15) == 0) && ((uintptr_t)w->d_w & 15) == 0, "conv_umma: operands must be 16-byte aligned");
 
+  const bvg_tuning T = tune_of(d->tune);
+  const int umma_mb = T.umma_mb, umma_wide_mb2 = T.umma_wide_mb2, umma_max_ctas = T.umma_max_ctas, umma_tap_group = T.umma_tap_group,
+            umma_a_stages = T.umma_a_stages;
   UmmaParams& p = out->p;
   memset(&p, 0, sizeof(p));
   int rc = fill_epilogue(d, p.epi);
@@ -974,7 +973,7 @@ int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out) {
                                  (umma_wide_mb2 > 0 || (umma_wide_mb2 == 0 && planes == 2 && p.col_stride == 256));
     const bool tmem_ok = cand * p.col_stride * 2 <= 512 || (cand == 1) || single_stage_ok;
     if (!tmem_ok) continue;
-    if (plan_smem(cand, 2, max_span, planes, w_rows, max_taps, &br, &nb, &tg) < (cand == 1 ? 2 : 3)) continue;
+    if (plan_smem(umma_tap_group, cand, 2, max_span, planes, w_rows, max_taps, &br, &nb, &tg) < (cand == 1 ? 2 : 3)) continue;
     const long long tiles = (long long)d->B * ceil_div(d->L, cand * UM_BM) * w->n_tiles;
     if (cand > 1 && tiles < 2ll * sms) continue;
     mb = cand;
@@ -994,18 +993,18 @@ int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out) {
   int a_stages = 2;
   for (int cand = UM_MAX_A_STAGES; cand > 2; --cand) {
     int br, nb, tg;
-    if (umma_a_stages == -1 && p.n_cb <= 2 && plan_smem(mb, cand, max_span, planes, w_rows, max_taps, &br, &nb, &tg) >= 3) {
+    if (umma_a_stages == -1 && p.n_cb <= 2 && plan_smem(umma_tap_group, mb, cand, max_span, planes, w_rows, max_taps, &br, &nb, &tg) >= 3) {
       a_stages = cand;
       break;
     }
   }
   if (fused) {  // the producer of tile i+1 runs under the MMAs of tile i: one spare stage when it fits
     int br, nb, tg;
-    if (plan_smem(mb, 3, max_span, planes, w_rows, max_taps, &br, &nb, &tg) >= 3) a_stages = 3;
+    if (plan_smem(umma_tap_group, mb, 3, max_span, planes, w_rows, max_taps, &br, &nb, &tg) >= 3) a_stages = 3;
   }
   if (umma_a_stages >= 2 && umma_a_stages <= UM_MAX_A_STAGES) a_stages = umma_a_stages;
   p.a_stages = a_stages;
-  const int bs = plan_smem(mb, a_stages, max_span, planes, w_rows, max_taps, &p.a_box_rows, &p.a_boxes, &p.tap_group);
+  const int bs = plan_smem(umma_tap_group, mb, a_stages, max_span, planes, w_rows, max_taps, &p.a_box_rows, &p.a_boxes, &p.tap_group);
   BVG_REQUIRE(bs >= 2, "conv_umma: tile does not fit in shared memory (mb %d, span %d, n_tile %d, planes %d)", mb, max_span, w->n_tile, planes);
   p.b_stages = bs;
   p.a_plane_bytes = p.a_boxes * p.a_box_rows * 128;

@@ -120,8 +120,8 @@ __global__ void pack_bias_kernel(const float* __restrict__ bias, int cout, int n
   out[n] = (n < n_total && bias != nullptr) ? bias[n % cout] : 0.f;
 }
 
-int umma_ntile_cap = 256;  // tuning hook: widest UMMA N tile chosen by conv_geometry (multiple of 16)
-int umma_stack = 128;      // tuning hook: widest n_tile whose (hi, lo) weight planes are stacked along N (0 = never)
+// bvg_tuning knobs read here (bvg_conv_geom.tune): umma_ntile_cap = widest UMMA N tile chosen by conv_geometry (multiple
+// of 16), umma_stack = widest n_tile whose (hi, lo) weight planes are stacked along N (0 = never)
 
 static int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -135,6 +135,7 @@ int conv_geometry(const bvg_conv_geom* g, bvg_conv_weights* w) {
   BVG_REQUIRE(tr ? g->stride > 0 : g->dilation > 0, "conv geometry: bad stride/dilation");
   const int fold = g->fold > 1 ? g->fold : 1;
   BVG_REQUIRE(fold == 1 || (!tr && g->backend == BVG_UMMA), "conv geometry: time folding is for Conv1d on the UMMA backend");
+  const int umma_ntile_cap = tune_of(g->tune).umma_ntile_cap, umma_stack = tune_of(g->tune).umma_stack;
   w->backend = g->backend;
   w->cin = g->cin * fold;
   w->split = (g->backend == BVG_UMMA && g->split) ? 1 : 0;

@@ -167,6 +167,9 @@ class _PackedConv:
         self.geom = L.ConvGeom(
             int(conv.transposed), conv.cin, conv.cout, conv.ksize, conv.dilation, conv.stride, conv.padding, backend, int(split), 0, self.fold
         )
+        tune = L.tuning_ptr()
+        if tune is not None:
+            self.geom.tune = tune
         wb, bb = C.c_size_t(), C.c_size_t()
         L.check(lib.bvg_conv_pack_bytes(C.byref(self.geom), C.byref(wb), C.byref(bb)), "conv_pack_bytes")
         self.desc = L.ConvWeights()
@@ -442,6 +445,7 @@ class Generator(nn.Module):
 
         labels = []
         esz = {L.F32: 4, L.BF16: 2, L.SPLIT: 4}
+        tune = L.tuning_ptr()  # test / A-B knobs of the binding (NULL when at their defaults); the program copies them
 
         def amp_desc(name, x, B_, L_, C_):
             a, invb, up, down = pk["act"][name]
@@ -451,6 +455,8 @@ class Generator(nn.Module):
             d.taps_up = (C.c_float * 12)(*up)
             d.taps_down = (C.c_float * 12)(*down)
             d.B, d.L, d.C, d.fast_sin = B_, L_, C_, fast_sin
+            if tune is not None:
+                d.tune = tune
             return d
 
         def conv_op(name, x, out, B_, L_, res=None, acc=None, div=1.0, pre_amp=None):
@@ -476,6 +482,8 @@ class Generator(nn.Module):
             assert L_ % fold == 0
             d.div, d.B, d.L = float(div), B_, L_ // fold
             d.w = C.pointer(pk["conv"][name].desc)
+            if tune is not None:
+                d.tune = tune
             ops.append(op)
 
         def amp_conv(aname, x, cname, out, B_, L_, C_, **epi):
@@ -499,6 +507,8 @@ class Generator(nn.Module):
             d.taps_up = (C.c_float * 12)(*up)
             d.taps_down = (C.c_float * 12)(*down)
             d.B, d.L, d.C, d.fast_sin = B_, L_, C_, fast_sin
+            if tune is not None:
+                d.tune = tune
             ops.append(op)
 
         # stage geometry

@@ -54,6 +54,9 @@ def activation1d(x, a, invb, taps_up, taps_down, in_dtype=L.F32, out_dtype=L.F32
     d.taps_up = (C.c_float * 12)(*[float(t) for t in taps_up])
     d.taps_down = (C.c_float * 12)(*[float(t) for t in taps_down])
     d.B, d.L, d.C, d.fast_sin = B, Ln, Ch, int(fast_sin)
+    tune = L.tuning_ptr()
+    if tune is not None:
+        d.tune = tune
     with torch.cuda.device(x.device):
         L.check(L.lib().bvg_amp_fwd(C.byref(d), _stream(x.device)), "amp_fwd")
     return from_buf(yb, x.shape)
@@ -98,6 +101,9 @@ def conv(x, pc: _PackedConv, *, x_dtype=None, out_dtype=L.F32, res=None, res_dty
     d.acc_in = ab.tensor() if ab is not None else _NULL
     d.div, d.B, d.L = float(div), B, Ln
     d.w = C.pointer(pc.desc)
+    tune = L.tuning_ptr()
+    if tune is not None:
+        d.tune = tune
     if pre_amp is not None:
         a, invb, taps_up, taps_down, fast_sin = pre_amp
         a = a.contiguous().float()
@@ -108,6 +114,8 @@ def conv(x, pc: _PackedConv, *, x_dtype=None, out_dtype=L.F32, res=None, res_dty
         ad.taps_up = (C.c_float * 12)(*[float(t) for t in taps_up])
         ad.taps_down = (C.c_float * 12)(*[float(t) for t in taps_down])
         ad.B, ad.L, ad.C, ad.fast_sin = B, Ln, Cx, int(fast_sin)
+        if tune is not None:
+            ad.tune = tune
         d.pre_amp = C.cast(C.pointer(ad), C.c_void_p)
     with torch.cuda.device(x.device):
         L.check(L.lib().bvg_conv_fwd(C.byref(d), _stream(x.device)), "conv_fwd")

@@ -556,6 +556,9 @@ def test_amp_guard_bands(ops, kernel, mode):
             L.set_tuning("amp_stream", 1 if kernel == "stream" else 0)
             L.set_tuning("amp_stream_bf16", 1 if kernel == "stream" else 0)
             L.set_tuning("amp_packed", 0 if kernel == "scalar" else 1)
+            tp = L.tuning_ptr()  # the knobs travel with the descriptor (bvg_amp_desc.tune)
+            if tp is not None:
+                d.tune = tp
             L.check(L.lib().bvg_amp_fwd(C.byref(d), torch.cuda.current_stream().cuda_stream), "amp_fwd")
             torch.cuda.synchronize()
         finally:

@@ -262,3 +262,43 @@ def test_load_mel_min_max_honours_reference_config_keys(tmp_path):
     with warnings.catch_warnings():
         warnings.simplefilter("error")
         np.testing.assert_array_equal(load_mel_min_max()[0], d_lo)  # no config: the shipped copy, silently
+
+
+def test_tuning_travels_with_descriptors():
+    """The library keeps no global knobs (include/bvg_b200.h, bvg_tuning): the binding's Tuning object is attached to
+    descriptors only when a knob differs from bvg_tuning_defaults(), and geometry reads it from bvg_conv_geom.tune."""
+    from svc_inference_pipeline_b200 import _lib as L
+
+    lib = L.lib()
+    assert not hasattr(lib, "bvg_set_tuning")
+    L.reset_tuning()
+    assert L.tuning_ptr() is None
+    t = L.Tuning()
+    lib.bvg_tuning_defaults(C.byref(t))
+    assert (t.amp_mma, t.amp_packed, t.amp_ct, t.umma_ntile_cap, t.umma_stack, t.amp_vec, t.umma_mb) == (1, 1, 1, 256, 128, 0, 0)
+    g, w = L.ConvGeom(0, 768, 768, 3, 1, 1, 1, L.UMMA, 0, 0), L.ConvWeights()
+    L.check(lib.bvg_conv_geometry(C.byref(g), C.byref(w)))
+    assert w.n_tile == 256
+    try:
+        L.set_tuning("umma_ntile_cap", 128)
+        assert L.tuning_ptr() is not None
+        g.tune = L.tuning_ptr()
+        L.check(lib.bvg_conv_geometry(C.byref(g), C.byref(w)))
+        assert w.n_tile == 128
+        with pytest.raises(L.BvgError):
+            L.set_tuning("no_such_knob", 1)
+    finally:
+        L.reset_tuning()
+    assert L.tuning_ptr() is None
+
+
+def test_product_mel_filterbank_is_the_pinned_one(golden):
+    """utils/mel.py::mel_filterbank (product, feeds bvg_logmel_fwd) == the basis make_golden.py committed after checking
+    it against transformers.audio_utils.mel_filter_bank(norm="slaney", mel_scale="slaney")."""
+    import torch  # noqa: F401  (utils.mel imports torch)
+
+    from svc_inference_pipeline_b200.utils.mel import mel_filterbank
+
+    np.testing.assert_array_equal(mel_filterbank(24000, 1024, 100, 0, 12000), golden("logmel.npz")["basis"])
+    fb = mel_filterbank(44100, 2048, 128, 0, 22050)
+    assert fb.shape == (128, 1025) and (fb >= 0).all() and (fb.sum(axis=1) > 0).all()

@@ -13,7 +13,7 @@ ap.add_argument("--precision", default="fp32")
 ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--frames", type=int, default=938)
 ap.add_argument("--out", default=None)
-ap.add_argument("--tune", action="append", default=[], help="name=value tuning knob (bvg_set_tuning)")
+ap.add_argument("--tune", action="append", default=[], help="name=value tuning knob (bvg_tuning, attached to every descriptor built afterwards)")
 ap.add_argument("--no-fold", action="store_true", help="narrow convolutions without time folding")
 ap.add_argument("--fuse", action="store_true", help="Activation1d fused into the narrow convolutions (Generator.fuse_amp, off by default)")
 a = ap.parse_args()

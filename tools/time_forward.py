@@ -14,7 +14,7 @@ ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--precisions", default="fp32,bf16")
 ap.add_argument("--v2", action="store_true", help="BASELINE configs[4]: 512x generator (input_dim 128, rates 8,4,2,2,2,2), hop 512 at 44.1 kHz; "
                                                   "one rank's share of B64 x 30 s on 8 GPUs is --batch 8 --frames 2584")
-ap.add_argument("--tune", action="append", default=[], help="name=value tuning knob (bvg_set_tuning)")
+ap.add_argument("--tune", action="append", default=[], help="name=value tuning knob (bvg_tuning, attached to every descriptor built afterwards)")
 ap.add_argument("--parts", default="0,2", help="overlap settings to time (0 = one stream, n = n batch parts on n streams)")
 a = ap.parse_args()
 from svc_inference_pipeline_b200 import _lib as _L
