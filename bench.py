@@ -404,6 +404,38 @@ def main():
         lat["api"] = "synthesis_audios(model, mel[100,379], cfg): H2D + forward + D2H + fade, wall clock"
         line["single_utterance_latency"] = lat
 
+    if rank == 0 and world == 1 and not args.no_extra:
+        # one DiffSVC denoiser step (the function infer.py's sampler calls 1000 times per utterance),
+        # reference mapper hyper-parameters, CUDA-graph replay, device-resident inputs
+        from svc_inference_pipeline_b200.modules.diffsvc import DiffSVC
+
+        mcfg = dict(noise_schedule_factors=[0.0001, 0.02, 1000], n_mel=100, residual_channels=384, diffusion_fc_size=128, conditioner_size=384,
+                    dilation_cycle_length=4, residual_kernel_size=3, residual_layer_num=20)
+        dm = DiffSVC(JsonHParams(**mcfg), precision="fp32")
+        dm.load_state_dict({k: torch.from_numpy(v) for k, v in synth.synthetic_diffsvc_state_dict(mcfg, seed=3).items()})
+        dm = dm.to(dev).eval()
+        dstep = {"what": "DiffSVC.forward(mel[B,L,100], cond[B,L,384], t[B,1]) on libbvg_b200 (20 dilated layers, C=384), one CUDA-graph replay per step; ms per step",
+                 "launches_per_step": dm.launches_per_step(1, 379)}
+        for prec in ("fp32", "bf16"):
+            dm.set_precision(prec)
+            for (b_, l_) in ((1, 379), (16, 938)):
+                xm = torch.randn(b_, l_, 100, device=dev)
+                xc = torch.randn(b_, l_, 384, device=dev)
+                tt = torch.full((b_, 1), 500, dtype=torch.long, device=dev)
+                for _ in range(3):
+                    dm(xm, xc, tt)
+                torch.cuda.synchronize(dev)
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(20):
+                    dm(xm, xc, tt)
+                a1.record()
+                torch.cuda.synchronize(dev)
+                dstep[f"{prec}_b{b_}x{l_}_ms"] = a0.elapsed_time(a1) / 20
+        line["diffsvc_step"] = dstep
+        del dm
+        torch.cuda.empty_cache()
+
     # ---- N > 1: the other BASELINE configs as extra keys (all ranks take part) -----------------------------
     if world > 1 and not args.no_extra and args.precision == "fp32":
         extra_steps = 2

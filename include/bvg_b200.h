@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BVG_ABI_VERSION 4  /* 2: bvg_conv_geom.fold, bvg_conv_desc.pre_amp; 3: bvg_stitch_fwd; 4: bvg_tuning in the descriptors (bvg_set_tuning removed), bvg_logmel_fwd */
+#define BVG_ABI_VERSION 4  /* 2: bvg_conv_geom.fold, bvg_conv_desc.pre_amp; 3: bvg_stitch_fwd; 4: bvg_tuning in the descriptors (bvg_set_tuning removed), bvg_logmel_fwd, bvg_rowop_fwd, bvg_diffembed_fwd, bvg_conv_desc.relu */
 
 enum bvg_status {
   BVG_OK = 0,
@@ -153,6 +153,9 @@ typedef struct bvg_conv_desc {
                                          ignored; pre_amp->y is not written.  The AMP-into-conv fusion of the narrow stages:
                                          modules/bigvgan.py:428-431  xt = c1(a1(x)); xt = c2(a2(xt)) */
   const bvg_tuning* tune; /* NULL = defaults */
+  int32_t relu;        /* 1: out = max(out, 0) as the last epilogue step (the F.relu after the 1x1 projections of the
+                          DiffSVC denoiser, modules/diffsvc.py:126, :316) */
+  int32_t _pad;
 } bvg_conv_desc;
 
 int bvg_conv_fwd(const bvg_conv_desc* d, void* stream);
@@ -270,6 +273,51 @@ typedef struct bvg_stitch_desc {
 int bvg_stitch_fwd(const bvg_stitch_desc* d, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * DiffSVC denoiser step (modules/diffsvc.py:192-232, :284-321 -- the function the
+ * sampler calls 1000 times per utterance, modules/diffsvcrepo_inference.py:234-235).  Its dense layers
+ * (dilated k=3 convolutions C -> 2C and the 1x1 projections) are tap GEMMs on bvg_conv_fwd; what is
+ * left are row-wise operations on channels-last [B, L, C] tensors and the step-embedding MLP:
+ *   BVG_ROW_ADDVEC: out[b,l,c] = x[b,l,c] + vec[b,c]      "y = x + diffusion_step" (:213), vec NULL = copy;
+ *                   channels C .. out_pitch-1 of out are zero-filled (operand padding)
+ *   BVG_ROW_GATE  : out[b,l,c] = sigmoid(x[b,l,c]) * tanh(x[b,l,C+c])   (:225-227; x has 2C channels)
+ *   BVG_ROW_SCALE : out[b,l,c] = x[b,l,c] / div           "skip / sqrt(n_layers)" (:313)
+ * x is F32 with row pitch x_pitch; out is F32, BF16 or SPLIT with row pitch out_pitch.
+ * ------------------------------------------------------------------------------------------ */
+enum bvg_rowop_kind { BVG_ROW_ADDVEC = 0, BVG_ROW_GATE = 1, BVG_ROW_SCALE = 2 };
+
+typedef struct bvg_rowop_desc {
+  int32_t kind; /* bvg_rowop_kind */
+  int32_t _pad;
+  const float* d_x;
+  const float* d_vec; /* ADDVEC: [B, C] or NULL */
+  bvg_tensor out;
+  float div;
+  int32_t B, L, C, x_pitch, out_pitch;
+} bvg_rowop_desc;
+
+int bvg_rowop_fwd(const bvg_rowop_desc* d, void* stream);
+
+/* Step encoder + every residual layer's diffusion projection in one launch (modules/diffsvc.py:69-93 StepEncoder.forward
+ * with an integer step, :205 ResidualBlock.diffusion_projection):
+ *   e = d_table[step[b]]  (the sin / cos lookup table, built on the host like the reference builds its buffer);
+ *   h = silu(W2 silu(W1 e + b1) + b2);   d_out[i][b][:] = Wd[i] h + bd[i]   for the n_layers layers.
+ * Weights are torch Linear layouts ([out, in] row-major); d_wd = [n_layers][C][fc], d_bd = [n_layers][C]. */
+typedef struct bvg_diffembed_desc {
+  const int32_t* d_step; /* [B] */
+  const float* d_table;  /* [max_steps][emb] */
+  const float* d_w1;     /* [fc][emb] */
+  const float* d_b1;
+  const float* d_w2;     /* [fc][fc] */
+  const float* d_b2;
+  const float* d_wd;
+  const float* d_bd;
+  float* d_out;          /* [n_layers][B][C] */
+  int32_t B, emb, fc, C, n_layers, max_steps;
+} bvg_diffembed_desc;
+
+int bvg_diffembed_fwd(const bvg_diffembed_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Log-mel front end (replaces mel_spectrogram, utils/mel.py:130-174, which the
  * reference runs with torch.stft + a librosa mel basis on the host: reflect pad (n_fft - hop) / 2, frames
  * every hop with center = False, periodic hann window of `win` samples, sqrt(re^2 + im^2 + 1e-9), basis
@@ -298,7 +346,8 @@ int bvg_convert(const bvg_tensor* src, const bvg_tensor* dst, size_t n_elems, vo
  * Programs: a whole Generator.forward (modules/bigvgan.py:600-622) as one pre-validated launch
  * list, so the per-call host work is one C call (and the list can be captured in a CUDA graph).
  * ------------------------------------------------------------------------------------------ */
-enum bvg_op_kind { BVG_OP_PACK = 0, BVG_OP_AMP = 1, BVG_OP_CONV = 2, BVG_OP_POST = 3 };
+enum bvg_op_kind { BVG_OP_PACK = 0, BVG_OP_AMP = 1, BVG_OP_CONV = 2, BVG_OP_POST = 3, BVG_OP_ROWOP = 4, BVG_OP_DIFFEMBED = 5 };
+#define BVG_N_OP_KINDS 6
 
 typedef struct bvg_op {
   int32_t kind; /* bvg_op_kind */
@@ -308,6 +357,8 @@ typedef struct bvg_op {
     bvg_amp_desc amp;
     bvg_conv_desc conv;
     bvg_post_desc post;
+    bvg_rowop_desc rowop;
+    bvg_diffembed_desc diffembed;
   } u;
 } bvg_op;
 
@@ -316,7 +367,7 @@ typedef struct bvg_program bvg_program;
 int bvg_program_create(const bvg_op* ops, int32_t n_ops, bvg_program** out);
 int bvg_program_run(bvg_program* p, void* stream);
 /* Same launches with a CUDA event between consecutive ops; synchronises the stream and returns the
- * device time (ms) and launch count per bvg_op_kind (arrays of 4).  Measurement aid for bench.py. */
+ * device time (ms) and launch count per bvg_op_kind (arrays of BVG_N_OP_KINDS).  Measurement aid for bench.py. */
 int bvg_program_run_timed(bvg_program* p, void* stream, float* ms_by_kind, int32_t* n_by_kind,
                           float* ms_per_op /* optional, n_ops entries */);
 /* Issue n programs with the same op sequence op by op, program k on streams[k].  Each stream keeps its own

@@ -14,7 +14,9 @@ LIB_PATH = os.environ.get("BVG_B200_LIB") or os.path.join(_HERE, "libbvg_b200.so
 
 F32, BF16, SPLIT = 0, 1, 2
 SIMT, UMMA = 0, 1
-OP_PACK, OP_AMP, OP_CONV, OP_POST = 0, 1, 2, 3
+OP_PACK, OP_AMP, OP_CONV, OP_POST, OP_ROWOP, OP_DIFFEMBED = 0, 1, 2, 3, 4, 5
+N_OP_KINDS = 6
+ROW_ADDVEC, ROW_GATE, ROW_SCALE = 0, 1, 2
 MAX_TAPS, MAX_NTILES = 16, 32
 ABI_VERSION = 4
 
@@ -82,6 +84,8 @@ class ConvDesc(C.Structure):
         ("w", C.POINTER(ConvWeights)),
         ("pre_amp", C.c_void_p),  # const bvg_amp_desc*: Activation1d fused in front of the convolution (or NULL)
         ("tune", C.POINTER(Tuning)),
+        ("relu", C.c_int32),
+        ("_pad", C.c_int32),
     ]
 
 
@@ -174,8 +178,29 @@ class LogmelDesc(C.Structure):
     ]
 
 
+class RowopDesc(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("_pad", C.c_int32),
+        ("d_x", C.c_void_p),
+        ("d_vec", C.c_void_p),
+        ("out", Tensor),
+        ("div", C.c_float),
+        ("B", C.c_int32),
+        ("L", C.c_int32),
+        ("C", C.c_int32),
+        ("x_pitch", C.c_int32),
+        ("out_pitch", C.c_int32),
+    ]
+
+
+class DiffEmbedDesc(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("d_step", "d_table", "d_w1", "d_b1", "d_w2", "d_b2", "d_wd", "d_bd", "d_out")] + [
+        (n, C.c_int32) for n in ("B", "emb", "fc", "C", "n_layers", "max_steps")]
+
+
 class _OpUnion(C.Union):
-    _fields_ = [("pack", PackDesc), ("amp", AmpDesc), ("conv", ConvDesc), ("post", PostDesc)]
+    _fields_ = [("pack", PackDesc), ("amp", AmpDesc), ("conv", ConvDesc), ("post", PostDesc), ("rowop", RowopDesc), ("diffembed", DiffEmbedDesc)]
 
 
 class Op(C.Structure):
@@ -202,6 +227,8 @@ EXPORTS = [
     "bvg_tail_fwd",
     "bvg_stitch_fwd",
     "bvg_logmel_fwd",
+    "bvg_rowop_fwd",
+    "bvg_diffembed_fwd",
     "bvg_convert",
     "bvg_program_create",
     "bvg_program_run",
@@ -238,6 +265,8 @@ def lib():
         "bvg_tail_fwd": [C.POINTER(TailDesc), C.c_void_p],
         "bvg_stitch_fwd": [C.POINTER(StitchDesc), C.c_void_p],
         "bvg_logmel_fwd": [C.POINTER(LogmelDesc), C.c_void_p],
+        "bvg_rowop_fwd": [C.POINTER(RowopDesc), C.c_void_p],
+        "bvg_diffembed_fwd": [C.POINTER(DiffEmbedDesc), C.c_void_p],
         "bvg_convert": [C.POINTER(Tensor), C.POINTER(Tensor), C.c_size_t, C.c_void_p],
         "bvg_conv_geometry": [C.POINTER(ConvGeom), C.POINTER(ConvWeights)],
         "bvg_conv_pack_bytes": [C.POINTER(ConvGeom), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)],

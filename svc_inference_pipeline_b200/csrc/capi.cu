@@ -43,6 +43,8 @@ int pack_mel(const bvg_pack_desc* d, cudaStream_t st);
 int tail_forward(const bvg_tail_desc* d, cudaStream_t st);
 int stitch_forward(const bvg_stitch_desc* d, cudaStream_t st);
 int logmel_forward(const bvg_logmel_desc* d, cudaStream_t st);
+int rowop_forward(const bvg_rowop_desc* d, cudaStream_t st);
+int diffembed_forward(const bvg_diffembed_desc* d, cudaStream_t st);
 int convert(const bvg_tensor* src, const bvg_tensor* dst, size_t n, cudaStream_t st);
 int conv_geometry(const bvg_conv_geom* g, bvg_conv_weights* w);
 size_t conv_plane_elems(const bvg_conv_weights* w);
@@ -109,6 +111,8 @@ int bvg_conv_fwd(const bvg_conv_desc* d, void* stream) { return bvg::conv_forwar
 int bvg_post_fwd(const bvg_post_desc* d, void* stream) { return bvg::post_forward(d, (cudaStream_t)stream); }
 int bvg_pack_mel(const bvg_pack_desc* d, void* stream) { return bvg::pack_mel(d, (cudaStream_t)stream); }
 int bvg_tail_fwd(const bvg_tail_desc* d, void* stream) { return bvg::tail_forward(d, (cudaStream_t)stream); }
+int bvg_rowop_fwd(const bvg_rowop_desc* d, void* stream) { return bvg::rowop_forward(d, (cudaStream_t)stream); }
+int bvg_diffembed_fwd(const bvg_diffembed_desc* d, void* stream) { return bvg::diffembed_forward(d, (cudaStream_t)stream); }
 int bvg_logmel_fwd(const bvg_logmel_desc* d, void* stream) { return bvg::logmel_forward(d, (cudaStream_t)stream); }
 int bvg_stitch_fwd(const bvg_stitch_desc* d, void* stream) { return bvg::stitch_forward(d, (cudaStream_t)stream); }
 int bvg_convert(const bvg_tensor* src, const bvg_tensor* dst, size_t n, void* stream) {
@@ -183,7 +187,7 @@ int bvg_program_create(const bvg_op* ops, int32_t n_ops, bvg_program** out) {
           return rc;
         }
       }
-    } else if (op.kind != BVG_OP_PACK && op.kind != BVG_OP_AMP && op.kind != BVG_OP_POST) {
+    } else if (op.kind != BVG_OP_PACK && op.kind != BVG_OP_AMP && op.kind != BVG_OP_POST && op.kind != BVG_OP_ROWOP && op.kind != BVG_OP_DIFFEMBED) {
       bvg::set_error("program_create: op %d has unknown kind %d", i, op.kind);
       delete p;
       return BVG_EINVAL;
@@ -202,6 +206,8 @@ static int run_one(bvg_program* p, size_t i, cudaStream_t st) {
     case BVG_OP_CONV:
       return p->umma[i] ? bvg::conv_umma_launch(reinterpret_cast<const bvg::UmmaLaunch*>(p->umma[i]), st) : bvg::conv_forward(&op.u.conv, st);
     case BVG_OP_POST: return bvg::post_forward(&op.u.post, st);
+    case BVG_OP_ROWOP: return bvg::rowop_forward(&op.u.rowop, st);
+    case BVG_OP_DIFFEMBED: return bvg::diffembed_forward(&op.u.diffembed, st);
     default: return BVG_EINVAL;
   }
 }
@@ -257,7 +263,7 @@ int bvg_program_run_timed(bvg_program* p, void* stream, float* ms_by_kind, int32
   }
   cudaEventRecord(ev[n], st);
   cudaError_t e = cudaStreamSynchronize(st);
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < BVG_N_OP_KINDS; ++k) {
     ms_by_kind[k] = 0.f;
     n_by_kind[k] = 0;
   }
@@ -267,7 +273,7 @@ int bvg_program_run_timed(bvg_program* p, void* stream, float* ms_by_kind, int32
       cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
       const int k = p->ops[i].kind;
       if (ms_per_op) ms_per_op[i] = ms;
-      if (k >= 0 && k < 4) {
+      if (k >= 0 && k < BVG_N_OP_KINDS) {
         ms_by_kind[k] += ms;
         n_by_kind[k] += 1;
       }

@@ -775,6 +775,10 @@ __global__ void __launch_bounds__(FUSED ? UM_THREADS_FUSED : UM_THREADS, 1) conv
 #pragma unroll
                 for (int j = 0; j < 4; ++j) v[i][j] = __fdiv_rn(v[i][j], p.epi.div);
               }
+              if (GEN && p.epi.relu) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[i][j] = fmaxf(v[i][j], 0.f);
+              }
               const long long off = off0 + (long long)(8 * i) * N;
               if (out_dt == BVG_F32) {
                 *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.epi.out) + off) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
@@ -1061,7 +1065,7 @@ static UmmaKernel select_kernel(const UmmaParams& p) {
   const bool res = e.res != nullptr, acc = e.acc != nullptr;
   const bool sbf = (res && e.res_dtype == BVG_BF16) || (acc && e.acc_dtype == BVG_BF16);
   const bool mixed = (res && acc && e.res_dtype != e.acc_dtype);
-  const bool plain = p.vec_ok && !mixed && (acc || !e.use_div) && (!acc || res);
+  const bool plain = p.vec_ok && !mixed && (acc || !e.use_div) && (!acc || res) && !e.relu;
   if (p.f_x) {  // fused Activation1d producer: the epilogues the fp32 path's resblock convolutions use, else the generic one
     if (plain && !sbf) {
       if (e.out_dtype == BVG_F32 && !res) return conv_umma_kernel<BVG_F32, false, false, false, false, true>;

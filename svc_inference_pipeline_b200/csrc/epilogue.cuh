@@ -17,6 +17,7 @@ struct EpiParams {
   float div;
   int out_dtype, res_dtype, acc_dtype;
   int use_div;
+  int relu;  // max(v, 0) after everything else
   int N;  // row pitch of out / res / acc (elements)
 };
 
@@ -79,6 +80,10 @@ __device__ __forceinline__ void epilogue4(const EpiParams& e, long long row, int
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = __fdiv_rn(v[i], e.div);
   }
+  if (e.relu) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
   if (e.out_dtype == BVG_F32) {
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + off) = make_float4(v[0], v[1], v[2], v[3]);
   } else if (e.out_dtype == BVG_BF16) {
@@ -99,6 +104,7 @@ __device__ __forceinline__ void epilogue1(const EpiParams& e, long long row, int
   if (e.res) v += epi_load1(e.res, e.res_dtype, off);
   if (e.acc) v += epi_load1(e.acc, e.acc_dtype, off);
   if (e.use_div) v = __fdiv_rn(v, e.div);
+  if (e.relu) v = fmaxf(v, 0.f);
   if (e.out_dtype == BVG_F32) {
     reinterpret_cast<float*>(e.out)[off] = v;
   } else if (e.out_dtype == BVG_BF16) {
@@ -122,6 +128,7 @@ inline int fill_epilogue(const bvg_conv_desc* d, EpiParams& e) {
   e.bias = d->w->d_bias;
   e.div = d->div;
   e.use_div = (d->div != 1.0f && d->div != 0.0f) ? 1 : 0;
+  e.relu = d->relu ? 1 : 0;
   e.N = d->w->n_total;
   BVG_REQUIRE(e.out != nullptr, "conv: null output");
   BVG_REQUIRE(e.out_dtype >= BVG_F32 && e.out_dtype <= BVG_SPLIT, "conv: bad output dtype");

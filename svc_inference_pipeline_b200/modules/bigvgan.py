@@ -628,8 +628,8 @@ class Generator(nn.Module):
         prog = self._program(B, T)
         n = prog.launches
         per = (C.c_float * n)()
-        ms = (C.c_float * 4)()
-        cnt = (C.c_int32 * 4)()
+        ms = (C.c_float * L.N_OP_KINDS)()
+        cnt = (C.c_int32 * L.N_OP_KINDS)()
         acc = [0.0] * n
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
@@ -648,14 +648,14 @@ class Generator(nn.Module):
         keeps whatever the last forward left in it."""
         dev = self._require_cuda()
         prog = self._program(B, T)
-        ms = (C.c_float * 4)()
-        cnt = (C.c_int32 * 4)()
-        tot = [0.0] * 4
+        ms = (C.c_float * L.N_OP_KINDS)()
+        cnt = (C.c_int32 * L.N_OP_KINDS)()
+        tot = [0.0] * L.N_OP_KINDS
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             for _ in range(max(1, reps)):
                 L.check(L.lib().bvg_program_run_timed(prog.handle, stream, ms, cnt, None), "program_run_timed")
-                for k in range(4):
+                for k in range(L.N_OP_KINDS):
                     tot[k] += ms[k] / max(1, reps)
         return {
             "conv_ms": tot[L.OP_CONV], "conv_n": cnt[L.OP_CONV], "amp_ms": tot[L.OP_AMP], "amp_n": cnt[L.OP_AMP],

@@ -31,6 +31,8 @@ __all__ = [
     "mel_range",
     "count_parameters",
     "aa_filter_taps",
+    "diffsvc_state_dict_spec",
+    "synthetic_diffsvc_state_dict",
 ]
 
 
@@ -182,6 +184,54 @@ def synthetic_state_dict(vcfg, seed: int = 0, recipe: str = "repo") -> "OrderedD
             v = sd[name[: -len("_g")] + "_v"]
             norm = np.sqrt((v.astype(np.float64) ** 2).sum(axis=(1, 2), keepdims=True))
             sd[name] = (norm * np.exp2(2.0 * g_spread * (rng.random(shape) - 0.5))).astype(np.float32)
+    return sd
+
+
+def diffsvc_state_dict_spec(mcfg) -> "OrderedDict[str, tuple]":
+    """``name -> (shape, kind, fan_in)`` of the reference DiffSVC denoiser's ``state_dict()`` (``modules/diffsvc.py:235-282``;
+    the step-embedding table is a non-persistent buffer and is not part of it)."""
+    n_mel, ch = int(_get(mcfg, "n_mel")), int(_get(mcfg, "residual_channels"))
+    fc, cond = int(_get(mcfg, "diffusion_fc_size")), int(_get(mcfg, "conditioner_size"))
+    k, nl = int(_get(mcfg, "residual_kernel_size")), int(_get(mcfg, "residual_layer_num"))
+    spec: "OrderedDict[str, tuple]" = OrderedDict()
+
+    def conv(prefix, cout, cin, ks):
+        spec[prefix + ".weight"] = ((cout, cin, ks), "conv_w", cin * ks)
+        spec[prefix + ".bias"] = ((cout,), "bias", cin * ks)
+
+    def linear(prefix, out, inp):
+        spec[prefix + ".weight"] = ((out, inp), "lin_w", inp)
+        spec[prefix + ".bias"] = ((out,), "bias", inp)
+
+    conv("mel_preprocess.projection", ch, n_mel, 1)
+    linear("diffusion_embedding.projection1", fc, 128)
+    linear("diffusion_embedding.projection2", fc, fc)
+    for i in range(nl):
+        p = f"residual_layers.{i}"
+        conv(p + ".dilated_conv", 2 * ch, ch, k)
+        linear(p + ".diffusion_projection", ch, fc)
+        conv(p + ".conditioner_projection", 2 * ch, cond, 1)
+        conv(p + ".output_projection", 2 * ch, ch, 1)
+    conv("skip_projection", ch, ch, 1)
+    conv("output_projection", n_mel, ch, 1)
+    return spec
+
+
+def synthetic_diffsvc_state_dict(mcfg, seed: int = 0) -> "OrderedDict[str, np.ndarray]":
+    """Seeded random-init DiffSVC denoiser state_dict (float32, numpy-only, bit-reproducible): convolutions
+    ``N(0, 2 / fan_in)`` like the reference's ``kaiming_normal_`` (``modules/diffsvc.py:23-26``), linear layers and biases
+    ``U(-1/sqrt(fan_in), 1/sqrt(fan_in))`` like PyTorch's defaults.  The final ``output_projection.weight`` -- zero at
+    construction in the reference (``:280``), which would make the whole network invisible in the output -- is drawn
+    ``N(0, 1 / fan_in)`` as a trained checkpoint would have it."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    sd: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    for name, (shape, kind, fan_in) in diffsvc_state_dict_spec(mcfg).items():
+        if kind == "conv_w":
+            std = math.sqrt((1.0 if name == "output_projection.weight" else 2.0) / fan_in)
+            sd[name] = _normal(rng, shape, std)
+        else:
+            b = 1.0 / math.sqrt(fan_in)
+            sd[name] = _uniform(rng, shape, -b, b)
     return sd
 
 

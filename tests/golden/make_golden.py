@@ -313,9 +313,39 @@ def golden_logmel():
     save("logmel.npz", wave=wave, logmel=m, basis=fb)
 
 
+def golden_diffsvc():
+    """DiffSVC denoiser step (SURVEY.md section 8f row 3): the UNMODIFIED reference ``modules/diffsvc.py::DiffSVC`` with the
+    reference's own mapper hyper-parameters (config/config.json:54-65) and the procedural state_dict of
+    utils/synth.py::synthetic_diffsvc_state_dict (the mapper checkpoint is absent), fp32 and fp64."""
+    from modules import diffsvc as ref_d
+
+    cfg = load_config(os.path.join(REF, "config", "config.json"))
+    keys = ["noise_schedule_factors", "n_mel", "residual_channels", "diffusion_fc_size", "conditioner_size", "dilation_cycle_length", "residual_kernel_size", "residual_layer_num"]
+    mcfg = {k: cfg.mapper[k] for k in keys}
+    model = ref_d.DiffSVC(JsonHParams(**mcfg)).eval()
+    sd = synth.synthetic_diffsvc_state_dict(mcfg, seed=3)
+    ref_sd = model.state_dict()
+    assert list(ref_sd.keys()) == list(sd.keys()), "DiffSVC state_dict key grammar/order mismatch"
+    for k, v in sd.items():
+        assert tuple(ref_sd[k].shape) == v.shape, (k, ref_sd[k].shape, v.shape)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    out = dict(n_params=sum(p.numel() for p in model.parameters()), keys_sha256=np.frombuffer(hashlib.sha256("\n".join(f"{k}:{tuple(v.shape)}" for k, v in ref_sd.items()).encode()).digest(), dtype=np.uint8))
+    for tag, (B, Ln, steps) in {"b2": (2, 61, [17, 903]), "utt": (1, 379, [500])}.items():
+        mel = rnd((B, Ln, mcfg["n_mel"]), 50 + B)
+        cond = rnd((B, Ln, mcfg["conditioner_size"]), 60 + B)
+        t = torch.tensor(steps, dtype=torch.long).unsqueeze(1)
+        y32, _ = model(torch.from_numpy(mel), torch.from_numpy(cond), t)
+        model.double()
+        y64, _ = model(torch.from_numpy(mel).double(), torch.from_numpy(cond).double(), t)
+        model.float()
+        out.update({tag + "_mel": mel, tag + "_cond": cond, tag + "_steps": np.asarray(steps), tag + "_y": y32.numpy(), tag + "_y_f64": y64.numpy()})
+        print(f"diffsvc {tag}: reference fp32 vs fp64 max-abs {np.abs(y32.numpy() - y64.numpy()).max():.3e}, |y|max {np.abs(y64.numpy()).max():.3f}")
+    save("diffsvc.npz", **out)
+
+
 STEPS = {
     "mel_range": mel_range_fixture, "filters": golden_filters, "activation": golden_activation, "convs": golden_convs, "tiny": golden_tiny,
-    "repo": golden_repo, "bench_item": golden_bench_item, "v2_long": golden_v2_long, "recipes": golden_recipes, "logmel": golden_logmel,
+    "repo": golden_repo, "bench_item": golden_bench_item, "v2_long": golden_v2_long, "recipes": golden_recipes, "logmel": golden_logmel, "diffsvc": golden_diffsvc,
 }
 
 if __name__ == "__main__":
