@@ -23,6 +23,10 @@
 // Index arithmetic is pinned by the lane-level emulation tests/amp_mma_emulation.py.
 #include "amp_mma.cuh"
 
+#ifndef BVG_AMP_PAIR
+#define BVG_AMP_PAIR 1  // interior tiles: two time blocks in flight per warp (0 = one at a time, for A/B builds)
+#endif
+
 namespace bvg {
 
 // IN_BF16: x is bf16 (one operand plane) else fp32 (hi, lo planes).  OUT_MODE: BVG_BF16 | BVG_SPLIT.
@@ -241,6 +245,103 @@ __global__ void __launch_bounds__(32 * NG) amp_mma_kernel(const __grid_constant_
       return true;
     };
     static_assert(AM_NB % 2 == 0, "ping-pong needs an even number of z-tiles per staged tile");
+#if BVG_AMP_PAIR
+    if constexpr (!EDGE) {
+      // Interior tiles: two z-tiles per iteration with their two s-blocks computed side by side -- two independent
+      // ldmatrix -> HMMA -> snake -> HMMA chains in flight per warp instead of one (the stalls ncu showed were
+      // dependent-issue waits on exactly that chain).  Same arithmetic in the same order per element: bit-identical.
+#pragma unroll 1
+      for (int i = 0; i < AM_NB; i += 2) {
+        const int m = mt + i;
+        SFrag c0, c1;
+        {
+          [[maybe_unused]] uint32_t xh0[4], xh1[4], xl0[4], xl1[4];
+          amm::ldmatrix_x4_trans(addr, xh0);
+          amm::ldmatrix_x4_trans(addr + 8 * PITCH, xh1);
+          if constexpr (NPL == 2) {
+            amm::ldmatrix_x4_trans(addr + PLANE, xl0);
+            amm::ldmatrix_x4_trans(addr + 8 * PITCH + PLANE, xl1);
+          }
+          float d0[2][4], d1[2][4];
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) d0[h][r] = d1[h][r] = 0.f;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            amm::mma_bf16(d0[h], xh0, up_hi[h]);
+            amm::mma_bf16(d1[h], xh1, up_hi[h]);
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            amm::mma_bf16(d0[h], xh0, up_lo[h]);
+            amm::mma_bf16(d1[h], xh1, up_lo[h]);
+          }
+          if constexpr (NPL == 2) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              amm::mma_bf16(d0[h], xl0, up_hi[h]);
+              amm::mma_bf16(d1[h], xl1, up_hi[h]);
+            }
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            amm::snake_pair<FAST_SIN>(d0[h][0], d0[h][1], apar[0], invb[0]);
+            amm::snake_pair<FAST_SIN>(d1[h][0], d1[h][1], apar[0], invb[0]);
+            amm::snake_pair<FAST_SIN>(d0[h][2], d0[h][3], apar[1], invb[1]);
+            amm::snake_pair<FAST_SIN>(d1[h][2], d1[h][3], apar[1], invb[1]);
+          }
+          auto pack = [&](const float (&d)[2][4], SFrag& out) {
+            if constexpr (S_F16) {
+              out.hi[0] = amm::pack_f16x2_sat(d[0][0], d[0][1]);
+              out.hi[1] = amm::pack_f16x2_sat(d[0][2], d[0][3]);
+              out.hi[2] = amm::pack_f16x2_sat(d[1][0], d[1][1]);
+              out.hi[3] = amm::pack_f16x2_sat(d[1][2], d[1][3]);
+            } else {
+              amm::split_pair(d[0][0], d[0][1], out.hi[0], out.lo[0]);
+              amm::split_pair(d[0][2], d[0][3], out.hi[1], out.lo[1]);
+              amm::split_pair(d[1][0], d[1][1], out.hi[2], out.lo[2]);
+              amm::split_pair(d[1][2], d[1][3], out.hi[3], out.lo[3]);
+            }
+          };
+          pack(d0, c0);
+          pack(d1, c1);
+        }
+        float za[4] = {0.f, 0.f, 0.f, 0.f}, za2[4] = {0.f, 0.f, 0.f, 0.f}, zb[4] = {0.f, 0.f, 0.f, 0.f}, zb2[4] = {0.f, 0.f, 0.f, 0.f};
+        down(za, fa, 0);
+        down(zb, c0, 0);
+        down(za2, c0, 1);
+        down(zb2, c1, 1);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          za[r] += za2[r];
+          zb[r] += zb2[r];
+        }
+        if constexpr (NOUT == 2) {
+          uint32_t h0, l0, h1, l1;
+          amm::split_pair(za[0], za[1], h0, l0);
+          amm::split_pair(za[2], za[3], h1, l1);
+          amm::stmatrix_x4_trans(st_addr, h0, h1, l0, l1);
+          amm::split_pair(zb[0], zb[1], h0, l0);
+          amm::split_pair(zb[2], zb[3], h1, l1);
+          amm::stmatrix_x4_trans(st_addr + STG, h0, h1, l0, l1);
+        } else {
+          amm::stmatrix_x2_trans(st_addr, pack_bf16x2(za[0], za[1]), pack_bf16x2(za[2], za[3]));
+          amm::stmatrix_x2_trans(st_addr + STG, pack_bf16x2(zb[0], zb[1]), pack_bf16x2(zb[2], zb[3]));
+        }
+        __syncwarp();
+        if (rb_on) {
+          const uint4 va = *reinterpret_cast<const uint4*>(rb_ptr), vb = *reinterpret_cast<const uint4*>(rb_ptr + STG);
+          *reinterpret_cast<uint4*>(out_base + (long long)(8 * m + 3 + rb_row) * C) = va;
+          *reinterpret_cast<uint4*>(out_base + (long long)(8 * m + 11 + rb_row) * C) = vb;
+        }
+        __syncwarp();  // the staging rows are rewritten by the next iteration
+        fa = c1;
+        addr += 16 * PITCH;
+      }
+      return;
+    }
+#endif
 #pragma unroll 1
     for (int i = 0; i < AM_NB; i += 2) {
       if (!step(i, fa, fb)) break;
