@@ -339,13 +339,14 @@ __global__ void __launch_bounds__(32 * NG) amp_mma_kernel(const __grid_constant_
         fa = c1;
         addr += 16 * PITCH;
       }
-      return;
-    }
+    } else
 #endif
+    {
 #pragma unroll 1
-    for (int i = 0; i < AM_NB; i += 2) {
-      if (!step(i, fa, fb)) break;
-      if (!step(i + 1, fb, fa)) break;
+      for (int i = 0; i < AM_NB; i += 2) {
+        if (!step(i, fa, fb)) break;
+        if (!step(i + 1, fb, fa)) break;
+      }
     }
   };
 

@@ -52,6 +52,12 @@ int pack_conv_weights(const bvg_conv_geom* g, const float* d_v, const float* d_g
                       float* d_scale_scratch, cudaStream_t st);
 int pack_post_weights(const float* d_v, const float* d_g, int cin, int ksize, float* d_w_out, float* d_scale_scratch, cudaStream_t st);
 
+struct PairLaunch;
+bool conv_pair_eligible(const bvg_conv_desc* d);
+int conv_pair_prepare(const bvg_conv_desc* d, PairLaunch* out);
+int conv_pair_launch(const PairLaunch* l, cudaStream_t st);
+int conv_pair_forward(const bvg_conv_desc* d, cudaStream_t st);
+size_t pair_launch_size();
 struct UmmaLaunch;
 int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out);
 int conv_umma_launch(const UmmaLaunch* l, cudaStream_t st);
@@ -61,7 +67,7 @@ static int conv_forward(const bvg_conv_desc* d, cudaStream_t st) {
   BVG_REQUIRE(d && d->w, "conv: null descriptor");
   BVG_REQUIRE(!d->pre_amp || d->w->backend == BVG_UMMA, "conv: a fused Activation1d (pre_amp) needs the UMMA backend");
   if (d->w->backend == BVG_SIMT) return conv_simt_forward(d, st);
-  if (d->w->backend == BVG_UMMA) return conv_umma_forward(d, st);
+  if (d->w->backend == BVG_UMMA) return conv_pair_eligible(d) ? conv_pair_forward(d, st) : conv_umma_forward(d, st);
   set_error("conv: unknown backend %d", d->w->backend);
   return BVG_EINVAL;
 }
@@ -75,11 +81,13 @@ struct bvg_program {
   std::vector<bvg_conv_weights*> owned_weights;
   std::vector<bvg_tuning*> owned_tunings;   // deep copies of the descriptors' bvg_tuning (the caller's may go away)
   std::vector<void*> umma;  // UmmaLaunch* per op (nullptr for the others)
+  std::vector<void*> pair;  // PairLaunch* per op: convolutions that run on the CTA-pair kernel
   int launches = 0;
   ~bvg_program() {
     for (auto* w : owned_weights) delete w;
     for (auto* t : owned_tunings) delete t;
     for (auto* u : umma) ::operator delete(u);
+    for (auto* u : pair) ::operator delete(u);
   }
 };
 
@@ -154,6 +162,7 @@ int bvg_program_create(const bvg_op* ops, int32_t n_ops, bvg_program** out) {
   }
   p->ops.assign(ops, ops + n_ops);
   p->umma.assign(n_ops, nullptr);
+  p->pair.assign(n_ops, nullptr);
   for (int i = 0; i < n_ops; ++i) {
     bvg_op& op = p->ops[i];
     if (op.kind == BVG_OP_AMP && op.u.amp.tune) {
@@ -178,7 +187,15 @@ int bvg_program_create(const bvg_op* ops, int32_t n_ops, bvg_program** out) {
         delete p;
         return BVG_EINVAL;
       }
-      if (w->backend == BVG_UMMA) {
+      if (w->backend == BVG_UMMA && bvg::conv_pair_eligible(&op.u.conv)) {
+        void* rec = ::operator new(bvg::pair_launch_size());
+        p->pair[i] = rec;
+        int rc = bvg::conv_pair_prepare(&op.u.conv, reinterpret_cast<bvg::PairLaunch*>(rec));
+        if (rc != BVG_OK) {
+          delete p;
+          return rc;
+        }
+      } else if (w->backend == BVG_UMMA) {
         void* rec = ::operator new(bvg::umma_launch_size());
         p->umma[i] = rec;
         int rc = bvg::conv_umma_prepare(&op.u.conv, reinterpret_cast<bvg::UmmaLaunch*>(rec));
@@ -204,6 +221,7 @@ static int run_one(bvg_program* p, size_t i, cudaStream_t st) {
     case BVG_OP_PACK: return bvg::pack_mel(&op.u.pack, st);
     case BVG_OP_AMP: return bvg::amp_forward(&op.u.amp, st);
     case BVG_OP_CONV:
+      if (p->pair[i]) return bvg::conv_pair_launch(reinterpret_cast<const bvg::PairLaunch*>(p->pair[i]), st);
       return p->umma[i] ? bvg::conv_umma_launch(reinterpret_cast<const bvg::UmmaLaunch*>(p->umma[i]), st) : bvg::conv_forward(&op.u.conv, st);
     case BVG_OP_POST: return bvg::post_forward(&op.u.post, st);
     case BVG_OP_ROWOP: return bvg::rowop_forward(&op.u.rowop, st);

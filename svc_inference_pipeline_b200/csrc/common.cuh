@@ -42,6 +42,7 @@ inline bvg_tuning default_tuning() {
   t.amp_ct = 1;
   t.umma_ntile_cap = 256;
   t.umma_stack = 128;
+  t.umma_pair = 1;
   return t;
 }
 inline bvg_tuning tune_of(const bvg_tuning* t) { return t ? *t : default_tuning(); }

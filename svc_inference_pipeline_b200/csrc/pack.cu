@@ -135,7 +135,7 @@ int conv_geometry(const bvg_conv_geom* g, bvg_conv_weights* w) {
   BVG_REQUIRE(tr ? g->stride > 0 : g->dilation > 0, "conv geometry: bad stride/dilation");
   const int fold = g->fold > 1 ? g->fold : 1;
   BVG_REQUIRE(fold == 1 || (!tr && g->backend == BVG_UMMA), "conv geometry: time folding is for Conv1d on the UMMA backend");
-  const int umma_ntile_cap = tune_of(g->tune).umma_ntile_cap, umma_stack = tune_of(g->tune).umma_stack;
+  const int umma_ntile_cap = tune_of(g->tune).umma_ntile_cap, umma_stack = tune_of(g->tune).umma_stack, umma_pair = tune_of(g->tune).umma_pair;
   w->backend = g->backend;
   w->cin = g->cin * fold;
   w->split = (g->backend == BVG_UMMA && g->split) ? 1 : 0;
@@ -161,7 +161,9 @@ int conv_geometry(const bvg_conv_geom* g, bvg_conv_weights* w) {
       // Measured on B200 (gpurun_out/r02_ops_fp32_b.txt): C = 768 same speed as 3 x 256, C = 384 9 % faster than 2 x 192;
       // C = 192 keeps its single 192-column tile (2 x 96 stacked is 8 % slower and K <= 2112 there)
       const int cap_max = (umma_ntile_cap >= 16 && umma_ntile_cap <= 256) ? umma_ntile_cap / 16 * 16 : 256;
-      int cap = (w->split && umma_stack >= 128 && cap_max > 128 && n_total > 256) ? 128 : cap_max;
+      // (with the CTA-pair kernel, conv_pair.cu, the wide layers keep 256 / 192-column tiles and two separate weight
+      // planes: there the correction products have their own accumulator columns without stacking)
+      int cap = (w->split && !umma_pair && umma_stack >= 128 && cap_max > 128 && n_total > 256) ? 128 : cap_max;
       for (;;) {
         const int base = (tr && g->cout % 16 == 0) ? g->cout : n_total;
         const int t = ceil_div(base, cap);

@@ -135,17 +135,35 @@ def test_conv_geometry_tables():
     w = geom(0, 768, 768, 11, 5, 1, 25, L.UMMA, 0, 0)
     assert (w.n_total, w.n_tile, w.n_tiles, w.cin_pad, w.x_pitch, w.tap_stride, w.split) == (768, 256, 3, 768, 768, 11, 0)
     assert list(w.shift[2])[:11] == [5 * (j - 5) for j in range(11)]
-    # split operands: wide layers take 128-column tiles with both weight planes stacked (split == 2), so that the
-    # correction products get their own accumulator columns; a single-tile layer (C = 192) keeps its 192 columns
+    # split operands: wide layers keep 256 / 192-column tiles and two weight planes for the CTA-pair kernel (conv_pair.cu,
+    # correction products in their own accumulator columns); without it (bvg_tuning.umma_pair = 0) they take 128-column
+    # tiles with both planes stacked (split == 2) for the same reason; narrow layers are always stacked
     w = geom(0, 768, 768, 11, 5, 1, 25, L.UMMA, 1, 0)
-    assert (w.n_total, w.n_tile, w.n_tiles, w.split) == (768, 128, 6, 2)
-    assert list(w.shift[5])[:11] == [5 * (j - 5) for j in range(11)]
+    assert (w.n_total, w.n_tile, w.n_tiles, w.split) == (768, 256, 3, 1)
     w = geom(0, 384, 384, 7, 1, 1, 3, L.UMMA, 1, 0)
-    assert (w.n_tile, w.n_tiles, w.split) == (128, 3, 2)
-    w = geom(0, 192, 192, 7, 1, 1, 3, L.UMMA, 1, 0)
-    assert (w.n_tile, w.n_tiles, w.split) == (192, 1, 1)
-    w = geom(1, 1536, 768, 16, 1, 8, 4, L.UMMA, 1, 0)  # v2 ups.0: 6144 columns would be 48 tiles of 128 -> stays at 256
-    assert (w.n_total, w.n_tile, w.n_tiles, w.split) == (6144, 256, 24, 1)
+    assert (w.n_tile, w.n_tiles, w.split) == (192, 2, 1)
+    w = geom(0, 96, 96, 7, 1, 1, 3, L.UMMA, 1, 0)
+    assert (w.n_tile, w.n_tiles, w.split) == (96, 1, 2)
+    try:
+        L.set_tuning("umma_pair", 0)
+
+        def geom0(*a):
+            g, w = L.ConvGeom(*a), L.ConvWeights()
+            g.tune = L.tuning_ptr()
+            L.check(lib.bvg_conv_geometry(C.byref(g), C.byref(w)))
+            return w
+
+        w = geom0(0, 768, 768, 11, 5, 1, 25, L.UMMA, 1, 0)
+        assert (w.n_total, w.n_tile, w.n_tiles, w.split) == (768, 128, 6, 2)
+        assert list(w.shift[5])[:11] == [5 * (j - 5) for j in range(11)]
+        w = geom0(0, 384, 384, 7, 1, 1, 3, L.UMMA, 1, 0)
+        assert (w.n_tile, w.n_tiles, w.split) == (128, 3, 2)
+        w = geom0(0, 192, 192, 7, 1, 1, 3, L.UMMA, 1, 0)
+        assert (w.n_tile, w.n_tiles, w.split) == (192, 1, 1)
+        w = geom0(1, 1536, 768, 16, 1, 8, 4, L.UMMA, 1, 0)  # v2 ups.0: 6144 columns would be 48 tiles of 128 -> stays at 256
+        assert (w.n_total, w.n_tile, w.n_tiles, w.split) == (6144, 256, 24, 1)
+    finally:
+        L.reset_tuning()
     w = geom(1, 1536, 768, 8, 1, 4, 2, L.UMMA, 0, 0)  # ups.0: phase r uses taps {-1,0} (r<2) or {0,1}
     assert (w.n_total, w.n_tile, w.n_tiles, w.tap_stride) == (3072, 256, 12, 2)
     assert [list(w.shift[t])[:2] for t in (0, 5, 6, 11)] == [[-1, 0], [-1, 0], [0, 1], [0, 1]]
@@ -275,7 +293,7 @@ def test_tuning_travels_with_descriptors():
     assert L.tuning_ptr() is None
     t = L.Tuning()
     lib.bvg_tuning_defaults(C.byref(t))
-    assert (t.amp_mma, t.amp_packed, t.amp_ct, t.umma_ntile_cap, t.umma_stack, t.amp_vec, t.umma_mb) == (1, 1, 1, 256, 128, 0, 0)
+    assert (t.amp_mma, t.amp_packed, t.amp_ct, t.umma_ntile_cap, t.umma_stack, t.umma_pair, t.amp_vec, t.umma_mb) == (1, 1, 1, 256, 128, 1, 0, 0)
     g, w = L.ConvGeom(0, 768, 768, 3, 1, 1, 1, L.UMMA, 0, 0), L.ConvWeights()
     L.check(lib.bvg_conv_geometry(C.byref(g), C.byref(w)))
     assert w.n_tile == 256
