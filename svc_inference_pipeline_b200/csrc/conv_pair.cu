@@ -146,8 +146,12 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_pair_kernel(const __grid_c
 
   const int planes = p.planes;
   const int half_rows = p.n_tile >> 1;                                   // weight rows this CTA holds per tap
-  const uint32_t corr_col = (uint32_t)p.col_stride;                      // correction accumulator (SPLIT)
-  const int stage_cols = (planes == 2 ? 2 : 1) * p.col_stride;
+  // SPLIT: the correction products go to their own columns (p.stacked = 1) or, for the single-tile C = 192 layers
+  // (K <= 2112: the main accumulator's extra additions cost 5e-6 there, and two accumulator stages matter more than
+  // that on their short tiles), into the main accumulator (p.stacked = 0)
+  const bool corr_separate = planes == 2 && p.stacked != 0;
+  const uint32_t corr_col = corr_separate ? (uint32_t)p.col_stride : 0u;
+  const int stage_cols = (corr_separate ? 2 : 1) * p.col_stride;
 
   if (warp == 0) {
     // ================================ TMA producer (both CTAs) ================================
@@ -202,7 +206,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_pair_kernel(const __grid_c
       const uint32_t tmem_main = tmem_base + (uint32_t)(as * stage_cols);
       const uint32_t tmem_corr = tmem_main + corr_col;
       const int* shifts = p.shift[nt];
-      uint32_t main_acc = 0u, corr_acc = 0u;  // 0 => the first product overwrites the accumulator
+      uint32_t main_acc = 0u, corr_acc = corr_separate ? 0u : 1u;  // 0 => the first product overwrites the accumulator
       for (int cb = 0; cb < p.n_cb; ++cb) {
         const int ksteps = cb + 1 < p.n_cb ? 4 : ks_last;
         ptx::mbar_wait(a_full(sa), pa, p.err_flag, 4);
@@ -257,7 +261,6 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_pair_kernel(const __grid_c
     const int g = lane & 3;
     const int n_my = (n_chunks - grp + 1) >> 1;  // chunks grp, grp + 2, ...
     const int N = p.epi.N;
-    const bool split = planes == 2;
     int as = 0, ap = 0;
     for (long long tile = pair; tile < p.total_tiles; tile += n_pairs) {
       const int nt = (int)(tile % p.n_tiles);
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_pair_kernel(const __grid_c
           if (tbase >= p.L) continue;  // whole 32-row slab past the end of the sequence (warp-uniform)
           uint32_t r[16];
           ptx::tmem_ld16(tmem_q + (uint32_t)c0, r);
-          if (split) {
+          if (corr_separate) {
             uint32_t r2[16];
             ptx::tmem_ld16(tmem_q + corr_col + (uint32_t)c0, r2);
             ptx::tmem_ld_wait();
@@ -418,10 +421,7 @@ bool conv_pair_eligible(const bvg_conv_desc* d) {
   if (tune_of(d->tune).umma_pair == 0) return false;
   if (!w || w->backend != BVG_UMMA || d->pre_amp || w->split == 2) return false;
   if (w->n_tile < 128 || w->n_tile % 32 != 0 || w->n_total % 4 != 0) return false;
-  // SPLIT operands with a single N tile (C = 192): main + correction accumulators leave one TMEM stage and the tiles are
-  // short (K = 3 slices), so the un-overlapped epilogue costs more than the pair saves (measured 12.0 vs 10.5 ms per
-  // forward for the C = 192 class, gpurun_out/r02 A/B); bf16 operands (two stages) gain there (4.05 vs 4.99 ms)
-  if (w->split && w->n_tiles == 1) return false;
+  if (w->split && w->n_tiles == 1 && tune_of(d->tune).umma_pair == 2) return false;  // A/B: C = 192 SPLIT layers on the single-CTA kernel
   if (d->relu) return false;
   const bool res = d->res.d_ptr != nullptr, acc = d->acc_in.d_ptr != nullptr;
   const bool use_div = d->div != 1.0f && d->div != 0.0f;
@@ -473,8 +473,14 @@ int conv_pair_prepare(const bvg_conv_desc* d, PairLaunch* out) {
     if (hi - lo > max_span) max_span = hi - lo;
   }
   p.col_stride = (w->n_tile + 31) / 32 * 32;
-  BVG_REQUIRE(planes * p.col_stride <= 512, "conv_pair: accumulators do not fit the tensor memory");
-  p.t_stages = 512 / (planes * p.col_stride);
+  // SPLIT: main + correction columns; a layer with a single N tile (C = 192: short tiles, K <= 2112) keeps ONE
+  // accumulator for all three products so that two stages fit and its epilogue overlaps the next tile (with main +
+  // correction on one stage it measured 12.0 ms per forward against 10.5 ms on the single-CTA kernel)
+  const bool corr_separate = planes == 2 && !(w->n_tiles == 1 && 2 * p.col_stride > 256);
+  p.stacked = corr_separate ? 1 : 0;
+  const int acc_cols = (corr_separate ? 2 : 1) * p.col_stride;
+  BVG_REQUIRE(acc_cols <= 512, "conv_pair: accumulators do not fit the tensor memory");
+  p.t_stages = 512 / acc_cols;
   if (p.t_stages > UM_MAX_T_STAGES) p.t_stages = UM_MAX_T_STAGES;
   p.tile_rows = 2 * UM_BM;  // per pair
   p.m_tiles_per_item = ceil_div(d->L, p.tile_rows);
