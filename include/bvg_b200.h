@@ -70,7 +70,8 @@ typedef struct bvg_tuning {
   int32_t umma_a_stages;   /* 0 = choose; activation stages (2..4) */
   int32_t umma_stack;      /* default 128: widest n_tile with stacked (hi, lo) weight planes (0 = never) */
   int32_t umma_pair;       /* default 1: wide convolutions (N tile >= 128) on the CTA-pair kernel (tcgen05.mma.cta_group::2);
-                              0: single-CTA kernel, wide SPLIT layers then pack as stacked 128-column tiles */
+                              0: single-CTA kernel, wide SPLIT layers then pack as stacked 128-column tiles;
+                              2: single-tile SPLIT layers (C = 192) on the single-CTA kernel; 4: wide SPLIT layers keep 256 / 192-column tiles */
 } bvg_tuning;
 
 void bvg_tuning_defaults(bvg_tuning* t);

@@ -85,6 +85,27 @@ __device__ __forceinline__ uint32_t make_idesc_m256(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 
+// MMAs of one weight stage with compile-time K steps (straight-line issue: the lone issuing warp executes a few dependent
+// uniform-datapath instructions per tcgen05.mma, which matters once an MMA lasts ~65 cycles)
+template <int KS>
+__device__ __forceinline__ void issue_whi(bool split, uint32_t tmem_main, uint32_t tmem_corr, uint64_t desc_hi, uint32_t a16, uint32_t a_plane16,
+                                          uint32_t b16, uint32_t idesc, uint32_t main_acc, uint32_t corr_acc) {
+#pragma unroll
+  for (int k = 0; k < KS; ++k) {
+    const uint64_t bd = desc_hi | (uint64_t)(b16 + 2u * k);
+    if (ptx::elect_one()) ptx2::umma2_f16(tmem_main, desc_hi | (uint64_t)(a16 + 2u * k), bd, idesc, k == 0 ? main_acc : 1u);
+    if (split) {
+      if (ptx::elect_one()) ptx2::umma2_f16(tmem_corr, desc_hi | (uint64_t)(a16 + a_plane16 + 2u * k), bd, idesc, k == 0 ? corr_acc : 1u);
+    }
+  }
+}
+template <int KS>
+__device__ __forceinline__ void issue_wlo(uint32_t tmem_corr, uint64_t desc_hi, uint32_t a16, uint32_t b16, uint32_t idesc) {
+#pragma unroll
+  for (int k = 0; k < KS; ++k)
+    if (ptx::elect_one()) ptx2::umma2_f16(tmem_corr, desc_hi | (uint64_t)(a16 + 2u * k), desc_hi | (uint64_t)(b16 + 2u * k), idesc, 1u);
+}
+
 // OUT / SBF / RES / ACC: the compile-time epilogue choices of conv_umma_kernel (N % 4 == 0 required: vec_ok)
 template <int OUT, bool SBF, bool RES, bool ACC>
 __global__ void __launch_bounds__(UM_THREADS, 1) conv_pair_kernel(const __grid_constant__ UmmaParams p) {
@@ -218,15 +239,12 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_pair_kernel(const __grid_c
           ptx::tc_fence_after();
           {
             const uint32_t b16 = (((b_base + sb * p.b_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t bd = desc_hi | (uint64_t)(b16 + 2u * k);
-              if (ptx::elect_one()) ptx2::umma2_f16(tmem_main, desc_hi | (uint64_t)(a16 + 2u * k), bd, idesc, main_acc);
-              main_acc = 1u;
-              if (split) {
-                if (ptx::elect_one()) ptx2::umma2_f16(tmem_corr, desc_hi | (uint64_t)(a16 + a_plane16 + 2u * k), bd, idesc, corr_acc);
-                corr_acc = 1u;
-              }
-            }
+            if (ksteps == 4) issue_whi<4>(split, tmem_main, tmem_corr, desc_hi, a16, a_plane16, b16, idesc, main_acc, corr_acc);
+            else if (ksteps == 2) issue_whi<2>(split, tmem_main, tmem_corr, desc_hi, a16, a_plane16, b16, idesc, main_acc, corr_acc);
+            else if (ksteps == 3) issue_whi<3>(split, tmem_main, tmem_corr, desc_hi, a16, a_plane16, b16, idesc, main_acc, corr_acc);
+            else issue_whi<1>(split, tmem_main, tmem_corr, desc_hi, a16, a_plane16, b16, idesc, main_acc, corr_acc);
+            main_acc = 1u;
+            corr_acc = 1u;
           }
           if (ptx::elect_one()) ptx2::umma2_commit_both(b_empty(sb));
           __syncwarp();
@@ -235,8 +253,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_pair_kernel(const __grid_c
             ptx::mbar_wait(b_full(sb), pb, p.err_flag, 5);
             ptx::tc_fence_after();
             const uint32_t b16 = (((b_base + sb * p.b_stage_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
-            for (int k = 0; k < ksteps; ++k)
-              if (ptx::elect_one()) ptx2::umma2_f16(tmem_corr, desc_hi | (uint64_t)(a16 + 2u * k), desc_hi | (uint64_t)(b16 + 2u * k), idesc, 1u);
+            if (ksteps == 4) issue_wlo<4>(tmem_corr, desc_hi, a16, b16, idesc);
+            else if (ksteps == 2) issue_wlo<2>(tmem_corr, desc_hi, a16, b16, idesc);
+            else if (ksteps == 3) issue_wlo<3>(tmem_corr, desc_hi, a16, b16, idesc);
+            else issue_wlo<1>(tmem_corr, desc_hi, a16, b16, idesc);
             if (ptx::elect_one()) ptx2::umma2_commit_both(b_empty(sb));
             __syncwarp();
             if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
@@ -364,10 +384,14 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_pair_kernel(const __grid_c
             if (ACC) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) v[i][j] += ac[i][j];
-              if (p.epi.use_div) {
+            }
+            if (p.epi.use_div) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) v[i][j] = __fdiv_rn(v[i][j], p.epi.div);
-              }
+              for (int j = 0; j < 4; ++j) v[i][j] = __fdiv_rn(v[i][j], p.epi.div);
+            }
+            if (p.epi.relu) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) v[i][j] = fmaxf(v[i][j], 0.f);
             }
             const long long off = off0 + (long long)(8 * i) * N;
             if (OUT == BVG_F32) {
@@ -421,16 +445,16 @@ bool conv_pair_eligible(const bvg_conv_desc* d) {
   if (tune_of(d->tune).umma_pair == 0) return false;
   if (!w || w->backend != BVG_UMMA || d->pre_amp || w->split == 2) return false;
   if (w->n_tile < 128 || w->n_tile % 32 != 0 || w->n_total % 4 != 0) return false;
+  if (w->split == 2) return false;
   if (w->split && w->n_tiles == 1 && tune_of(d->tune).umma_pair == 2) return false;  // A/B: C = 192 SPLIT layers on the single-CTA kernel
-  if (d->relu) return false;
   const bool res = d->res.d_ptr != nullptr, acc = d->acc_in.d_ptr != nullptr;
-  const bool use_div = d->div != 1.0f && d->div != 0.0f;
-  if ((res && acc && d->res.dtype != d->acc_in.dtype) || (use_div && !acc) || (acc && !res)) return false;
+  if (res && acc && d->res.dtype != d->acc_in.dtype) return false;
   const bool sbf = (res && d->res.dtype == BVG_BF16) || (acc && d->acc_in.dtype == BVG_BF16);
   const int o = d->out.dtype;
-  if (o == BVG_BF16) return !res || sbf;  // bf16 path: residual stream in bf16
+  if (o == BVG_BF16) return (!res && !acc) || (sbf && res);  // bf16 path: residual stream in bf16
   if (sbf) return false;
-  return (o == BVG_F32) || (o == BVG_SPLIT && (!res || acc));
+  if (o == BVG_F32) return true;
+  return o == BVG_SPLIT && ((!res && !acc) || (res && acc));
 }
 
 int conv_pair_prepare(const bvg_conv_desc* d, PairLaunch* out) {
@@ -533,13 +557,14 @@ static PairKernel select_pair_kernel(const UmmaParams& p) {
   const bool res = e.res != nullptr, acc = e.acc != nullptr;
   const bool sbf = (res && e.res_dtype == BVG_BF16) || (acc && e.acc_dtype == BVG_BF16);
   if (!sbf) {
-    if (e.out_dtype == BVG_F32 && !res) return conv_pair_kernel<BVG_F32, false, false, false>;
+    if (e.out_dtype == BVG_F32 && !res && !acc) return conv_pair_kernel<BVG_F32, false, false, false>;
     if (e.out_dtype == BVG_F32 && res && !acc) return conv_pair_kernel<BVG_F32, false, true, false>;
     if (e.out_dtype == BVG_F32 && res && acc) return conv_pair_kernel<BVG_F32, false, true, true>;
-    if (e.out_dtype == BVG_SPLIT && !res) return conv_pair_kernel<BVG_SPLIT, false, false, false>;
+    if (e.out_dtype == BVG_F32 && !res && acc) return conv_pair_kernel<BVG_F32, false, false, true>;
+    if (e.out_dtype == BVG_SPLIT && !res && !acc) return conv_pair_kernel<BVG_SPLIT, false, false, false>;
     if (e.out_dtype == BVG_SPLIT && res && acc) return conv_pair_kernel<BVG_SPLIT, false, true, true>;
   }
-  if (e.out_dtype == BVG_BF16 && !res) return conv_pair_kernel<BVG_BF16, true, false, false>;
+  if (e.out_dtype == BVG_BF16 && !res && !acc) return conv_pair_kernel<BVG_BF16, true, false, false>;
   if (e.out_dtype == BVG_BF16 && res && !acc) return conv_pair_kernel<BVG_BF16, true, true, false>;
   if (e.out_dtype == BVG_BF16 && res && acc) return conv_pair_kernel<BVG_BF16, true, true, true>;
   return nullptr;

@@ -164,6 +164,11 @@ int conv_geometry(const bvg_conv_geom* g, bvg_conv_weights* w) {
       // (with the CTA-pair kernel, conv_pair.cu, the wide layers keep 256 / 192-column tiles and two separate weight
       // planes: there the correction products have their own accumulator columns without stacking)
       int cap = (w->split && !umma_pair && umma_stack >= 128 && cap_max > 128 && n_total > 256) ? 128 : cap_max;
+      // SPLIT layers with several N tiles (C >= 384) take 128-column tiles on the pair kernel too: main + correction
+      // columns are then 256 per stage and TWO accumulator stages fit, so the epilogue overlaps the next tile (ncu on
+      // the one-stage 256 / 192-column tiles: 93 % / 87 % tensor-pipe active; measured per forward C = 384 20.6 -> 18.4 ms,
+      // C = 768 19.6 -> 19.1 ms).  umma_pair == 4 keeps the wide tiles (A/B).
+      if (w->split && umma_pair && umma_pair != 4 && n_total >= 384 && cap > 128) cap = 128;
       for (;;) {
         const int base = (tr && g->cout % 16 == 0) ? g->cout : n_total;
         const int t = ceil_div(base, cap);
@@ -180,7 +185,9 @@ int conv_geometry(const bvg_conv_geom* g, bvg_conv_weights* w) {
   // Narrow split layers: both weight planes in ONE operand, rows [0, n_tile) = hi, [n_tile, 2 n_tile) = lo
   // per tap ("stacked", split = 2).  A_hi x [W_hi; W_lo] is then a single MMA of width 2 n_tile, so a product
   // costs two reads of the A tile from shared memory instead of three (these layers are bound by exactly that).
-  if (w->split && n_tile <= umma_stack && n_tile <= 128) w->split = 2;
+  // (a 128-column tile that the CTA-pair kernel takes keeps two separate planes: each CTA of the pair loads half of a box)
+  const bool for_pair = umma_pair && n_tile >= 128 && n_tile % 32 == 0 && n_total % 4 == 0;
+  if (w->split && n_tile <= umma_stack && n_tile <= 128 && !for_pair) w->split = 2;
   const int n_tables = (g->backend == BVG_SIMT) ? 1 : w->n_tiles;
   BVG_REQUIRE(n_tables <= BVG_MAX_NTILES, "conv geometry: %d N tiles exceed BVG_MAX_NTILES", w->n_tiles);
   for (int t = 0; t < BVG_MAX_NTILES; ++t) {

@@ -135,13 +135,15 @@ def test_conv_geometry_tables():
     w = geom(0, 768, 768, 11, 5, 1, 25, L.UMMA, 0, 0)
     assert (w.n_total, w.n_tile, w.n_tiles, w.cin_pad, w.x_pitch, w.tap_stride, w.split) == (768, 256, 3, 768, 768, 11, 0)
     assert list(w.shift[2])[:11] == [5 * (j - 5) for j in range(11)]
-    # split operands: wide layers keep 256 / 192-column tiles and two weight planes for the CTA-pair kernel (conv_pair.cu,
-    # correction products in their own accumulator columns); without it (bvg_tuning.umma_pair = 0) they take 128-column
+    # split operands: wide layers keep two weight planes for the CTA-pair kernel (conv_pair.cu, correction products in their
+    # own accumulator columns); without it (bvg_tuning.umma_pair = 0) they take 128-column
     # tiles with both planes stacked (split == 2) for the same reason; narrow layers are always stacked
-    w = geom(0, 768, 768, 11, 5, 1, 25, L.UMMA, 1, 0)
-    assert (w.n_total, w.n_tile, w.n_tiles, w.split) == (768, 256, 3, 1)
+    w = geom(0, 768, 768, 11, 5, 1, 25, L.UMMA, 1, 0)   # pair kernel: 128 columns, two planes, main + correction x 2 stages
+    assert (w.n_total, w.n_tile, w.n_tiles, w.split) == (768, 128, 6, 1)
     w = geom(0, 384, 384, 7, 1, 1, 3, L.UMMA, 1, 0)
-    assert (w.n_tile, w.n_tiles, w.split) == (192, 2, 1)
+    assert (w.n_tile, w.n_tiles, w.split) == (128, 3, 1)
+    w = geom(0, 192, 192, 7, 1, 1, 3, L.UMMA, 1, 0)      # single tile: one accumulator for the three products, two stages
+    assert (w.n_tile, w.n_tiles, w.split) == (192, 1, 1)
     w = geom(0, 96, 96, 7, 1, 1, 3, L.UMMA, 1, 0)
     assert (w.n_tile, w.n_tiles, w.split) == (96, 1, 2)
     try:

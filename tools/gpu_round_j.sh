@@ -1,0 +1,7 @@
+#!/bin/bash
+set -u
+timeout 300 python -m pytest tests/test_gpu_ops.py -m gpu -q -x -k conv 2>&1 | tail -2
+for rep in 1 2; do
+  echo "== fp32 pair default"; timeout 300 python tools/profile_ops.py --precision fp32 | grep -E "#  conv  L(15008|30016|3752|938)|total="
+  echo "== fp32 pair umma_ntile_cap=128"; timeout 300 python tools/profile_ops.py --precision fp32 --tune umma_ntile_cap=128 | grep -E "#  conv  L(15008|30016|3752|938)|total="
+done
