@@ -322,7 +322,7 @@ def main():
     conv_tflops = conv_flops / (prof["conv_ms"] / 1e3) / 1e12
     amp_gbs = amp_bytes / (prof["amp_ms"] / 1e3) / 1e9
     passes = 3 if args.precision == "fp32" else 1
-    roofline = {"bound": "tensor", "kernel": f"conv_umma_kernel ({prof['conv_n']} launches/step)" if args.precision != "fp32_simt" else "conv_simt_kernel",
+    roofline = {"bound": "tensor", "kernel": f"tcgen05 tap-GEMM convolutions: conv_pair_kernel (cta_group::2, wide layers) + conv_umma_kernel (narrow layers), {prof['conv_n']} launches/step" if args.precision != "fp32_simt" else "conv_simt_kernel",
                 "achieved": conv_tflops, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": conv_tflops / peaks["tensor"],
                 "traffic": load_traffic("bf16" if args.precision == "bf16" else "fp32", "conv_umma_kernel"),
                 "issued_tflops": conv_tflops * passes, "issued_frac": conv_tflops * passes / peaks["tensor"],
