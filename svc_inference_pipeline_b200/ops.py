@@ -80,7 +80,7 @@ def pack_conv(v, g, bias, *, transposed=False, dilation=1, stride=1, padding=0, 
     return pc
 
 
-def conv(x, pc: _PackedConv, *, x_dtype=None, out_dtype=L.F32, res=None, res_dtype=L.F32, acc=None, acc_dtype=L.F32, div=1.0, pre_amp=None):
+def conv(x, pc: _PackedConv, *, x_dtype=None, out_dtype=L.F32, res=None, res_dtype=L.F32, acc=None, acc_dtype=L.F32, div=1.0, pre_amp=None, relu=False):
     """Tap-GEMM convolution of ``x [B, L, x_pitch]`` with packed weights; returns ``[B, L, n_total]``
     (for a transposed conv reshape to ``[B, L*u, Cout]``).  ``pre_amp = (a, invb, taps_up, taps_down, fast_sin)``
     fuses that Activation1d in front: ``x`` is then its fp32 input (``bvg_conv_desc.pre_amp``)."""
@@ -101,6 +101,7 @@ def conv(x, pc: _PackedConv, *, x_dtype=None, out_dtype=L.F32, res=None, res_dty
     d.acc_in = ab.tensor() if ab is not None else _NULL
     d.div, d.B, d.L = float(div), B, Ln
     d.w = C.pointer(pc.desc)
+    d.relu = int(relu)
     tune = L.tuning_ptr()
     if tune is not None:
         d.tune = tune

@@ -441,3 +441,42 @@ def test_checkpoint_recipes(golden, recipe):
     print(f"recipe {recipe}: fp32 path max-abs vs reference fp64: fast sin {errs[False]:.3e}, exact reduction {errs[True]:.3e} "
           f"(reference fp32 vs fp64 {float(np.abs(ref32 - ref64).max()):.3e}); bf16 path SNR {snr:.1f} dB, log-mel L1 {l1:.2e}")
     assert snr >= 20.0  # sanity only (see the docstring)
+
+
+def test_fused_activation_amblock2_does_not_alias(golden):
+    """AMPBlock2 with Generator.fuse_amp: after the first layer the block's output buffer is the Activation1d's own
+    input, where a fused producer would read halo rows other CTAs are overwriting -- the fusion is refused there
+     and the result equals the unfused forward and the reference."""
+    g = golden("tiny_generator.npz")
+    cfgd, sd = tiny_cfg_sd("b2_snakebeta_lin")
+    m = build(cfgd, sd, "fp32")
+    mel = torch.from_numpy(g["b2_snakebeta_lin_mel"]).to(DEV)
+    y_plain = m(mel).clone()
+    m.fuse_amp = True
+    m._invalidate()
+    y_fused = m(mel).clone()
+    labels = [lab for lab, kind, _ in m._program(1, mel.shape[-1], slot=(2, 2, 0)).labels if kind == "conv"]
+    fused = [lab for lab in labels if "+activations" in lab]
+    assert fused and all(lab.split()[0].endswith(".convs.0") for lab in fused), fused  # only the first layer of each block fuses
+    assert float((y_fused - y_plain).abs().max()) < 2e-6
+    assert np.abs(y_fused.cpu().numpy() - g["b2_snakebeta_lin_y_f64"]).max() < 1e-4
+
+
+def test_two_devices_in_one_process(golden):
+    """Function attributes (dynamic shared memory opt-in, carve-out) are per device: a second GPU driven from the same
+    process must get them too (the cache is keyed by (device, kernel))."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process")
+    g = golden("tiny_generator.npz")
+    cfgd, sd = tiny_cfg_sd("b1_snakebeta_log")
+    from svc_inference_pipeline_b200.modules.bigvgan import Generator
+    from svc_inference_pipeline_b200.utils.util import JsonHParams
+
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        m = Generator(JsonHParams(**cfgd), precision="fp32")
+        m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+        m = m.to(dev).eval()
+        outs.append(m(torch.from_numpy(g["b1_snakebeta_log_mel"]).to(dev)).cpu())
+    assert torch.equal(outs[0], outs[1])
+    assert np.abs(outs[1].numpy() - g["b1_snakebeta_log_y_f64"]).max() < 1e-4

@@ -620,7 +620,12 @@ def test_conv_guard_bands(ops, backend):
     split = backend == "umma_split"
     x_dt = L.F32 if backend == "simt" else (L.SPLIT if split else L.BF16)
     for (cin, cout, k, dil, stride, tr, B, Ln) in [(24, 24, 11, 5, 1, False, 2, 301), (48, 48, 7, 3, 1, False, 1, 130), (96, 48, 4, 1, 2, True, 2, 77),
-                                                  (200, 200, 3, 1, 1, False, 1, 257), (16, 8, 8, 1, 4, True, 3, 33)]:
+                                                  (200, 200, 3, 1, 1, False, 1, 257), (16, 8, 8, 1, 4, True, 3, 33),
+                                                  # CTA-pair kernel (N tile >= 128): a second 256-row pair tile with one valid row (the
+                                                  # peer CTA wholly past the end), 128-column SPLIT tiles, the single-tile C = 192 form,
+                                                  # a transposed conv with several N tiles
+                                                  (256, 256, 3, 1, 1, False, 1, 257), (384, 384, 3, 3, 1, False, 2, 131), (192, 192, 7, 5, 1, False, 1, 300),
+                                                  (384, 192, 4, 1, 2, True, 2, 129)]:
         shape = (cin, cout, k) if tr else (cout, cin, k)
         v = torch.from_numpy(rng.standard_normal(shape).astype(np.float32) * 0.1).to(DEV)
         g = v.flatten(1).norm(dim=1).reshape(-1, 1, 1) * 1.1
@@ -646,3 +651,72 @@ def test_conv_guard_bands(ops, backend):
             torch.cuda.synchronize()
             for pl in planes:
                 assert bool((pl[:G] == 321.0).all()) and bool((pl[-G:] == 321.0).all()), (backend, cin, cout, k, out_dt)
+
+
+PAIR_CASES = [
+    # (B, Cin, Cout, L, k, d, transposed, stride)
+    (2, 256, 256, 300, 3, 1, False, 1),    # two pair tiles per item, the second partial
+    (1, 384, 384, 1000, 7, 3, False, 1),   # SPLIT: 3 x 128-column tiles, two accumulator stages
+    (3, 192, 192, 129, 11, 5, False, 1),   # single tile: one accumulator for the three products
+    (1, 768, 768, 260, 3, 1, False, 1),    # 12 K slices
+    (2, 384, 192, 77, 4, 1, True, 2),      # transposed conv, per-tile tap tables
+    (1, 100, 256, 515, 7, 1, False, 1),    # conv_pre-like: Cin padded to 104, last K slice with 3 K steps
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES)
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("epi", ["plain", "res", "res_acc_div", "acc", "relu"])
+def test_conv_pair_vs_single_cta(ops, case, split, epi):
+    """conv_pair_kernel (tcgen05.mma.cta_group::2, the default for N tiles >= 128) against the single-CTA kernel on the
+    same layer (bvg_tuning.umma_pair = 0) and against the fp64 oracle: ragged lengths, several batch items, every
+    epilogue the pair kernel takes."""
+    _ops, L = ops
+    B, cin, cout, Ln, k, d, tr, u = case
+    rng = np.random.default_rng(cin + cout + Ln + k)
+    x = rng.standard_normal((B, cin, Ln)).astype(np.float32)
+    shape = (cin, cout, k) if tr else (cout, cin, k)
+    v = (rng.standard_normal(shape) / np.sqrt(cin * k)).astype(np.float32)
+    g = (np.sqrt((v.astype(np.float64) ** 2).sum(axis=(1, 2), keepdims=True)) * rng.uniform(0.7, 1.4, (shape[0], 1, 1))).astype(np.float32)
+    b = (rng.standard_normal(cout) * 0.1).astype(np.float32)
+    pad = (k - u) // 2 if tr else O.get_padding(k, d)
+    wts = [torch.from_numpy(t).to(DEV) for t in (v, g, b)]
+    w64 = O.weight_norm_fold(v.astype(np.float64), g.astype(np.float64))
+    ref = O.conv_transpose1d(x.astype(np.float64), w64, b.astype(np.float64), u, pad) if tr else O.conv1d(x.astype(np.float64), w64, b.astype(np.float64), d, pad)
+    Lo = ref.shape[-1]
+    extra = rng.standard_normal((2, B, cout, Lo)).astype(np.float32)
+    kw, want = {}, ref
+    if epi in ("res", "res_acc_div"):
+        kw["res"] = cl(extra[0]).reshape(B, Ln, -1)
+        want = want + extra[0]
+    if epi in ("res_acc_div", "acc"):
+        kw["acc"] = cl(extra[1]).reshape(B, Ln, -1)
+        want = want + extra[1]
+    if epi == "res_acc_div":
+        kw["div"] = 3.0
+        want = want / 3.0
+    if epi == "relu":
+        want = np.maximum(want, 0.0)
+
+    def run():
+        pc = _ops.pack_conv(*wts, transposed=tr, dilation=d, stride=u, padding=pad, backend=L.UMMA, split=split)
+        xl = cl(x)
+        if pc.x_pitch > cin:
+            xl = torch.nn.functional.pad(xl, (0, pc.x_pitch - cin))
+        y = _ops.conv(xl, pc, relu=(epi == "relu"), **kw)
+        return cf(y.reshape(B, Lo, cout)), pc
+
+    y_pair, pc = run()
+    if pc.desc.n_tile < 128:  # (a transposed conv whose per-phase width packs as 96-column tiles: single-CTA kernel)
+        assert tr and split
+        pytest.skip("this layer packs below the pair kernel's tile width")
+    assert pc.desc.split != 2
+    try:
+        L.set_tuning("umma_pair", 0)
+        y_single, _ = run()
+    finally:
+        L.reset_tuning()
+    scale = max(1.0, float(np.abs(want).max()))
+    tol = 3e-5 if split else 2e-2
+    assert np.abs(y_pair - want).max() < tol * scale, np.abs(y_pair - want).max()
+    assert np.abs(y_pair - y_single).max() < tol * scale
