@@ -301,11 +301,12 @@ int bvg_rowop_fwd(const bvg_rowop_desc* d, void* stream);
 
 /* Step encoder + every residual layer's diffusion projection in one launch (modules/diffsvc.py:69-93 StepEncoder.forward
  * with an integer step, :205 ResidualBlock.diffusion_projection):
- *   e = d_table[step[b]]  (the sin / cos lookup table, built on the host like the reference builds its buffer);
+ *   e = d_table[step[b]]  (the sin / cos lookup table, built on the host like the reference builds its buffer; a
+ *       fractional step interpolates between the two neighbouring rows);
  *   h = silu(W2 silu(W1 e + b1) + b2);   d_out[i][b][:] = Wd[i] h + bd[i]   for the n_layers layers.
  * Weights are torch Linear layouts ([out, in] row-major); d_wd = [n_layers][C][fc], d_bd = [n_layers][C]. */
 typedef struct bvg_diffembed_desc {
-  const int32_t* d_step; /* [B] */
+  const int32_t* d_step; /* [B] integer steps, or NULL when d_step_f is given */
   const float* d_table;  /* [max_steps][emb] */
   const float* d_w1;     /* [fc][emb] */
   const float* d_b1;
@@ -315,6 +316,7 @@ typedef struct bvg_diffembed_desc {
   const float* d_bd;
   float* d_out;          /* [n_layers][B][C] */
   int32_t B, emb, fc, C, n_layers, max_steps;
+  const float* d_step_f; /* [B] fractional steps (StepEncoder.lerp_embedding, modules/diffsvc.py:57-67): e = low + (high - low) * (t - floor t) */
 } bvg_diffembed_desc;
 
 int bvg_diffembed_fwd(const bvg_diffembed_desc* d, void* stream);

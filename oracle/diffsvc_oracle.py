@@ -1,7 +1,7 @@
 """CPU oracle for the DiffSVC denoiser step (TEST INFRASTRUCTURE ONLY -- never imported by the product path).
 
 Functional restatement of reference ``modules/diffsvc.py:284-321`` (``DiffSVC.forward``) with its sub-modules
-``StepEncoder.forward`` (``:69-93``, integer steps), ``SpectrogramPreprocessor.forward`` (``:118-128``) and
+``StepEncoder.forward`` (``:69-93``, integer and fractional steps), ``SpectrogramPreprocessor.forward`` (``:118-128``) and
 ``ResidualBlock.forward`` (``:192-232``), on the reference's own arithmetic library (PyTorch CPU), in float32 or
 float64, from a reference-format ``state_dict``.  Pinned by ``tests/golden/diffsvc.npz``, which
 ``tests/golden/make_golden.py`` writes by running the UNMODIFIED reference module on the same seeded state_dict.
@@ -39,7 +39,13 @@ def denoiser_forward(sd: dict, cfg, mel_spec: torch.Tensor, conditioner: torch.T
     # SpectrogramPreprocessor (:118-128)
     x = F.relu(F.conv1d(mel_spec.transpose(1, 2), w("mel_preprocess.projection.weight"), w("mel_preprocess.projection.bias")))
     # StepEncoder, integer steps (:79-91)
-    e = table[diffusion_step]                                                     # [B, 1, 128]
+    if diffusion_step.dtype in (torch.int32, torch.int64):
+        e = table[diffusion_step]                                                 # [B, 1, 128]
+    else:  # lerp_embedding (:57-67), per batch item (the reference's expression broadcasts [B, 1, 128] x [B, 1] to
+        # [B, B, 128] for B > 1 and only makes sense for one item; identical to it for B = 1)
+        t = diffusion_step.to(dt)
+        lo_i, hi_i = torch.floor(t).long(), torch.ceil(t).long()
+        e = table[lo_i] + (table[hi_i] - table[lo_i]) * (t - lo_i).unsqueeze(-1)
     e = F.silu(F.linear(e, w("diffusion_embedding.projection1.weight"), w("diffusion_embedding.projection1.bias")))
     e = F.silu(F.linear(e, w("diffusion_embedding.projection2.weight"), w("diffusion_embedding.projection2.bias")))
     skip = None

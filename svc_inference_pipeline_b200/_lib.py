@@ -196,7 +196,7 @@ class RowopDesc(C.Structure):
 
 class DiffEmbedDesc(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("d_step", "d_table", "d_w1", "d_b1", "d_w2", "d_b2", "d_wd", "d_bd", "d_out")] + [
-        (n, C.c_int32) for n in ("B", "emb", "fc", "C", "n_layers", "max_steps")]
+        (n, C.c_int32) for n in ("B", "emb", "fc", "C", "n_layers", "max_steps")] + [("d_step_f", C.c_void_p)]
 
 
 class _OpUnion(C.Union):

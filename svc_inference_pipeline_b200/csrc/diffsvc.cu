@@ -107,9 +107,19 @@ __global__ void __launch_bounds__(256) diffembed_kernel(const __grid_constant__ 
   float* h1 = e + p.emb;     // [fc]
   float* h2 = h1 + p.fc;     // [fc]
   const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  int step = p.d_step[b];
-  step = min(max(step, 0), p.max_steps - 1);
-  for (int k = threadIdx.x; k < p.emb; k += blockDim.x) e[k] = __ldg(p.d_table + (long long)step * p.emb + k);
+  if (p.d_step_f) {  // lerp_embedding (:57-67): low + (high - low) * (t - low_idx)
+    const float t = p.d_step_f[b];
+    const int lo = min(max((int)floorf(t), 0), p.max_steps - 1), hi = min(max((int)ceilf(t), 0), p.max_steps - 1);
+    const float w = t - (float)lo;
+    for (int k = threadIdx.x; k < p.emb; k += blockDim.x) {
+      const float a = __ldg(p.d_table + (long long)lo * p.emb + k), c = __ldg(p.d_table + (long long)hi * p.emb + k);
+      e[k] = a + (c - a) * w;
+    }
+  } else {
+    int step = p.d_step[b];
+    step = min(max(step, 0), p.max_steps - 1);
+    for (int k = threadIdx.x; k < p.emb; k += blockDim.x) e[k] = __ldg(p.d_table + (long long)step * p.emb + k);
+  }
   __syncthreads();
   for (int o = warp; o < p.fc; o += nw) {
     const float s = warp_dot(p.d_w1 + (long long)o * p.emb, e, p.emb, lane);
@@ -130,7 +140,7 @@ __global__ void __launch_bounds__(256) diffembed_kernel(const __grid_constant__ 
 }
 
 int diffembed_forward(const bvg_diffembed_desc* d, cudaStream_t st) {
-  BVG_REQUIRE(d && d->d_step && d->d_table && d->d_w1 && d->d_b1 && d->d_w2 && d->d_b2 && d->d_wd && d->d_bd && d->d_out, "diffembed: null pointer");
+  BVG_REQUIRE(d && (d->d_step || d->d_step_f) && d->d_table && d->d_w1 && d->d_b1 && d->d_w2 && d->d_b2 && d->d_wd && d->d_bd && d->d_out, "diffembed: null pointer");
   BVG_REQUIRE(d->B > 0 && d->emb > 0 && d->fc > 0 && d->C > 0 && d->n_layers > 0 && d->max_steps > 0, "diffembed: bad shape");
   const size_t smem = sizeof(float) * ((size_t)d->emb + 2 * (size_t)d->fc);
   BVG_REQUIRE(smem <= 48 * 1024, "diffembed: embedding / hidden sizes too large");

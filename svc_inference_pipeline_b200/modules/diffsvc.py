@@ -206,7 +206,7 @@ class DiffSVC(nn.Module):
         self._packed = pk
 
     # -- programs -----------------------------------------------------------------------------------
-    def _build(self, B: int, Ln: int):
+    def _build(self, B: int, Ln: int, float_steps: bool = False):
         if self._packed is None:
             self._pack()
         dev = self._device()
@@ -227,7 +227,7 @@ class DiffSVC(nn.Module):
 
         mel_in = torch.empty(B, Ln, self.n_mel, dtype=torch.float32, device=dev)
         cond_in = torch.empty(B, Ln, self.cond_size, dtype=torch.float32, device=dev)
-        step_in = torch.zeros(B, dtype=torch.int32, device=dev)
+        step_in = torch.zeros(B, dtype=torch.float32 if float_steps else torch.int32, device=dev)
         out = torch.empty(B, Ln, self.n_mel, dtype=torch.float32, device=dev)
         mel_op = _Buf(op_dt, rows * mel_pitch, dev)
         cond_op = _Buf(op_dt, rows * self.cond_size, dev)
@@ -273,7 +273,11 @@ class DiffSVC(nn.Module):
         op = L.Op()
         op.kind = L.OP_DIFFEMBED
         d = op.u.diffembed
-        d.d_step, d.d_table = step_in.data_ptr(), pk["table"].data_ptr()
+        if float_steps:
+            d.d_step_f = step_in.data_ptr()
+        else:
+            d.d_step = step_in.data_ptr()
+        d.d_table = pk["table"].data_ptr()
         d.d_w1, d.d_b1, d.d_w2, d.d_b2 = pk["w1"].data_ptr(), pk["b1"].data_ptr(), pk["w2"].data_ptr(), pk["b2"].data_ptr()
         d.d_wd, d.d_bd, d.d_out = pk["wd"].data_ptr(), pk["bd"].data_ptr(), dproj.data_ptr()
         d.B, d.emb, d.fc, d.C, d.n_layers, d.max_steps = B, pk["table"].shape[1], self.fc, Cc, nl, pk["table"].shape[0]
@@ -296,12 +300,12 @@ class DiffSVC(nn.Module):
         prog.cond_in, prog.step_in = cond_in, step_in
         return prog
 
-    def _program(self, B, Ln):
-        key = (B, Ln, self.precision)
+    def _program(self, B, Ln, float_steps=False):
+        key = (B, Ln, self.precision, bool(float_steps))
         prog = self._programs.get(key)
         if prog is None:
             with torch.cuda.device(self._device()):
-                prog = self._build(B, Ln)
+                prog = self._build(B, Ln, float_steps)
             if len(self._programs) >= 4:
                 self._programs.clear()
                 self._cond_key = None
@@ -315,7 +319,7 @@ class DiffSVC(nn.Module):
     @torch.no_grad()
     def forward(self, mel_spec: torch.Tensor, conditioner: torch.Tensor, diffusion_step):
         """Reference ``modules/diffsvc.py:284-321``.  ``mel_spec [B, L, n_mel]``, ``conditioner [B, L, cond]``,
-        ``diffusion_step [B, 1]`` (or ``[B]``) integer steps.  Returns ``(noise [B, L, n_mel], stats)``; ``stats`` (the
+        ``diffusion_step [B, 1]`` (or ``[B]``): integer steps (the sampler's ``t``) or fractional ones (interpolated embedding).  Returns ``(noise [B, L, n_mel], stats)``; ``stats`` (the
         reference's dictionary of intermediate tensors, which its sampler never reads) is empty."""
         dev = self._require_cuda()
         if mel_spec.dim() != 3 or mel_spec.shape[2] != self.n_mel:
@@ -324,12 +328,11 @@ class DiffSVC(nn.Module):
         if tuple(conditioner.shape) != (B, Ln, self.cond_size):
             raise ValueError(f"expected conditioner of shape [{B}, {Ln}, {self.cond_size}], got {tuple(conditioner.shape)}")
         step = torch.as_tensor(diffusion_step)
-        if step.dtype not in (torch.int32, torch.int64):
-            raise NotImplementedError("DiffSVC.forward takes integer diffusion steps (the sampler's t); the reference's lerp_embedding for fractional steps is not built")
+        float_steps = step.dtype not in (torch.int32, torch.int64)  # StepEncoder.forward :79-85: table lookup or lerp_embedding
         step = step.reshape(-1)
         if step.numel() == 1 and B > 1:
             step = step.expand(B)
-        prog = self._program(B, Ln)
+        prog = self._program(B, Ln, float_steps)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev)
             # same tensor OBJECT (weak reference: a freed tensor's address may be reused), unmodified since, same program
@@ -340,7 +343,7 @@ class DiffSVC(nn.Module):
                 prog.cond_prog.run(stream.cuda_stream)
                 self._cond_key = (weakref.ref(conditioner), conditioner._version, prog)
             prog.mel_in.copy_(mel_spec, non_blocking=True)
-            prog.step_in.copy_(step.to(torch.int32), non_blocking=True)
+            prog.step_in.copy_(step.to(prog.step_in.dtype), non_blocking=True)
             if self.use_cuda_graph:
                 if prog.graph is None:
                     prog.run(stream.cuda_stream)  # warm-up outside capture (lazy function attributes)

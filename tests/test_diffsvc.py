@@ -109,4 +109,10 @@ def test_denoiser_graph_steps_and_conditioner_cache(golden):
     assert np.abs(y3.cpu().numpy() - ref(mel, cond2, [17, 903])).max() < 1e-4
     y4, _ = m(mel, cond2, torch.tensor([17, 903], device=DEV))  # [B] steps, cached conditioner
     assert torch.equal(y3, y4)
+    # fractional steps: StepEncoder.lerp_embedding (modules/diffsvc.py:57-67)
+    tf = torch.tensor([[17.25], [902.5]])
+    y5, _ = m(mel, cond2, tf.to(DEV))
+    ref5 = DO.denoiser_forward(sd, MAPPER, mel.cpu().double(), cond2.cpu().double(), tf.double()).numpy()
+    assert np.abs(y5.cpu().numpy() - ref5).max() < 1e-4
+    assert float((y5 - y4).abs().max()) > 1e-3
     assert m.launches_per_step(2, 61) == 2 + 1 + 20 * 5 + 3
