@@ -295,7 +295,7 @@ def main():
     ms, per_rank = over_ranks(e0.elapsed_time(e1))
     value = world * audio_s_per_step * steps / (ms / 1e3)
     # the overlapped forward issues two half-batch programs (two streams) per step
-    launches = model.launches_per_forward(B, T) * (2 if (model.overlap_streams and B >= 2) else 1) * steps
+    launches = model.launches_per_forward(B, T) * (2 if model.overlaps(B) else 1) * steps
     y_item7 = y_last[7:8].cpu().numpy() if (rank == 0 and B > 7) else None
 
     # ---- e2e: the reference-facing call with host buffers ------------------------------------------
@@ -340,7 +340,7 @@ def main():
         "data": "synthetic (log-mel range of the reference's mel_min/max; random-init checkpoint, seed 0)",
         "config": {"workload": WORKLOAD if (B, T) == (BATCH_PER_GPU, FRAMES_PER_ITEM) else f"custom batch {B} x {T} frames", "batch_per_gpu": B, "frames": T,
                    "precision": args.precision, "l2": "activation working set (GBs) far exceeds the 126 MB L2; no flush needed",
-                   "streams": "two half-batches on two CUDA streams per rank, ops launched alternately" if (model.overlap_streams and B >= 2) else "one stream",
+                   "streams": "two half-batches on two CUDA streams per rank, ops launched alternately" if model.overlaps(B) else "one stream",
                    "parallelism": f"dp{world}: independent utterances per rank" + (", NCCL gather of the waveforms to rank 0 on a side stream (double-buffered) inside the step" if world > 1 else "")},
         "e2e": e2e, "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline, "roofline_amp": roofline_amp,
         "class_ms_per_step": {k: prof[k] for k in ("conv_ms", "amp_ms", "other_ms", "total_ms")},

@@ -271,7 +271,9 @@ class Generator(nn.Module):
         # Two half-batches on two streams, launched op by op in alternation: the tensor-core convolutions of
         # one half (one persistent CTA per SM, ~6 % of the issue slots) share the SMs with the FFMA-bound
         # Activation1d kernels of the other half.  Needs >= 2 utterances; results are identical.
-        self.overlap_streams = True
+        # None = per precision: on for the fp32 path (measured -4..-5 % step time, tools/time_forward.py: 85.7 -> 81.9 ms),
+        # off for the bf16 path (since the CTA-pair convolutions: 40.1-41.2 ms on one stream, 41.3-41.8 ms on two).
+        self.overlap_streams = None
         self.overlap_parts = 2
         self._side_streams = None
         self._mel_denorm = None  # (range, min) device tensors when forward() takes mels normalised to [-1, 1]
@@ -669,6 +671,12 @@ class Generator(nn.Module):
         output buffer, which the next forward of the same shape overwrites)."""
         return self.forward_borrowed(x).clone()
 
+    def overlaps(self, B: int) -> bool:
+        """Whether a batch of ``B`` runs as half-batch programs on two streams (``overlap_streams``; None = the
+        per-precision default)."""
+        on = self.overlap_streams if self.overlap_streams is not None else (self.precision != "bf16")
+        return bool(on) and B >= 2 and not self.use_cuda_graph
+
     @torch.no_grad()
     def forward_borrowed(self, x: torch.Tensor) -> torch.Tensor:
         """``forward`` without the final device copy: returns the program's own output buffer, valid until the next
@@ -680,7 +688,7 @@ class Generator(nn.Module):
         B, _, T = x.shape
         if B == 0 or T == 0:
             return torch.empty(B, 1, T * self.hop, dtype=torch.float32, device=dev)
-        if self.overlap_streams and B >= 2 and not self.use_cuda_graph:
+        if self.overlaps(B):
             return self._forward_overlapped(x, dev)
         prog = self._program(B, T)
         with torch.cuda.device(dev):

@@ -240,14 +240,14 @@ def test_overlapped_forward_is_identical(repo_model, B):
     from svc_inference_pipeline_b200.utils import synth
 
     mel = torch.from_numpy(synth.synthetic_mel(B, 100, 53, seed=31)).to(DEV)
-    assert repo_model.overlap_streams
+    assert repo_model.overlap_streams is None and repo_model.overlaps(B)  # fp32 path: on by default
     y_ov = repo_model(mel)
     y_ov2 = repo_model(mel)
     try:
         repo_model.overlap_streams = False
         y_plain = repo_model(mel)
     finally:
-        repo_model.overlap_streams = True
+        repo_model.overlap_streams = None
     assert y_ov.shape == (B, 1, 53 * 256)
     assert torch.equal(y_ov, y_plain) and torch.equal(y_ov, y_ov2)
 
