@@ -11,7 +11,7 @@ Drop-in for the generator half of the reference's ``modules/bigvgan.py`` (lines 
 
 Nothing is computed with PyTorch operators.  The module owns tensors (parameters, packed weights,
 activations workspace) and drives ``libbvg_b200.so`` through its C ABI: weight-norm is folded once
-at load, and one forward is a pre-built *program* of ~235 kernel launches (fused anti-aliased
+at load, and one forward is a pre-built *program* of 226 kernel launches (fused anti-aliased
 activations + tcgen05 tap-GEMM convolutions) issued by a single C call.  There is no CPU path.
 
 Numeric modes (``precision=``):

@@ -1,5 +1,5 @@
 """Short program for ncu: builds the repo generator and runs exactly two forwards at the bench shape
-(first = warm-up).  One forward = 235 launches: pack, conv_pre, 6 x (up-conv + 54 layer launches) ..."""
+(first = warm-up).  One forward = 226 launches: pack, conv_pre, 6 x (up-conv + 54 layer launches) ..."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -15,7 +15,7 @@ cfg = load_config(os.path.join(ROOT, "svc_inference_pipeline_b200", "config", "c
 m = Generator(cfg.vocoder, precision=precision)
 m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.synthetic_state_dict({k: cfg.vocoder[k] for k in cfg.vocoder.keys()}, 0).items()})
 m = m.cuda().eval()
-m.overlap_streams = False  # one program of the whole batch on one stream: 235 launches per forward, in program order
+m.overlap_streams = False  # one program of the whole batch on one stream: 226 launches per forward, in program order
 mel = torch.from_numpy(synth.synthetic_mel(B, 100, T, 1235)).cuda()
 for _ in range(2):
     y = m(mel)
