@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "svc_inference_pipeline_b200", "libbvg_b200.so")
-FAMILIES = ["UTCHMMA", "UTMALDG", "LDTM", "UTCBAR", "SYNCS", "HMMA", "FFMA2", "FMUL2", "FADD2", "FFMA", "MUFU", "LDGSTS", "LDSM", "STSM", "LDG", "STG"]
+FAMILIES = ["UTCHMMA.2CTA", "UTCHMMA", "UTMALDG", "LDTM", "UTCBAR", "SYNCS", "HMMA", "FFMA2", "FMUL2", "FADD2", "FFMA", "MUFU", "LDGSTS", "LDSM", "STSM", "LDG", "STG"]
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
 counts, total, name = collections.OrderedDict(), {}, None
 for ln in sass.splitlines():
@@ -21,10 +21,14 @@ for ln in sass.splitlines():
         counts[name] = collections.Counter()
         total[name] = 0
         continue
-    m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", ln)
+    m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", ln)
     if m and name:
         total[name] += 1
-        op = m.group(1)
+        full = m.group(1)
+        op = full.split(".")[0]
+        if full.startswith("UTCHMMA") and ".2CTA" in full:
+            counts[name]["UTCHMMA.2CTA"] += 1
+            continue
         for fam in FAMILIES:
             if op == fam or (op.startswith(fam) and fam not in ("FFMA", "LDG", "STG")) or (fam in ("FFMA", "LDG", "STG") and op == fam):
                 counts[name][fam] += 1
@@ -52,5 +56,5 @@ print("\nLargest instantiations of the two hot kernels:\n")
 print("| kernel | instr | " + " | ".join(FAMILIES) + " |")
 print("|---|---|" + "---|" * len(FAMILIES))
 for n in sorted(names, key=lambda q: -total[q]):
-    if any(s in short[n] for s in ("conv_umma_kernel", "amp_kernel_p2", "amp_mma_kernel")):
+    if any(s in short[n] for s in ("conv_pair_kernel", "conv_umma_kernel", "amp_kernel_p2", "amp_mma_kernel")):
         print(f"| {short[n]} | {total[n]} | " + " | ".join(str(counts[n][f]) if counts[n][f] else "" for f in FAMILIES) + " |")
