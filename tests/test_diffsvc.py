@@ -116,3 +116,32 @@ def test_denoiser_graph_steps_and_conditioner_cache(golden):
     assert np.abs(y5.cpu().numpy() - ref5).max() < 1e-4
     assert float((y5 - y4).abs().max()) > 1e-3
     assert m.launches_per_step(2, 61) == 2 + 1 + 20 * 5 + 3
+
+
+def test_denoiser_loader_reads_the_mapper_checkpoint(tmp_path):
+    """denoiser_model_loader takes the DiffSVC tensors (ModuleList index 1, reference utils/load_models.py:18-21) out of a
+    mapper checkpoint saved the way svc_model_loader expects it ({"state_dict": ...}, optional module. prefix)."""
+    import warnings
+
+    from svc_inference_pipeline_b200.utils.load_models import denoiser_model_loader
+
+    small = dict(MAPPER, residual_channels=16, conditioner_size=16, residual_layer_num=2, diffusion_fc_size=8)
+    sd = synth.synthetic_diffsvc_state_dict(small, seed=1)
+    ckpt = {"module.1." + k: torch.from_numpy(v) for k, v in sd.items()}
+    ckpt["module.0.content_encoder.weight"] = torch.zeros(3, 3)              # the condition encoders: not ours
+    ckpt["module.1.skip_projection.bias"] = torch.zeros(5)                   # wrong shape: dropped, reported
+    path = str(tmp_path / "mapper.pt")
+    torch.save({"state_dict": ckpt}, path)
+    cfg = JsonHParams(device="cpu", svc_model_path=path, mapper=small)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        m = denoiser_model_loader(cfg)
+    assert any("mismatched shape" in str(x.message) for x in w)
+    assert not m.training
+    rep = m.load_report
+    assert rep["missing"] == ["skip_projection.bias"] and rep["unknown"] == [] and rep["other_modules"] == ["0"]
+    assert [n for n, *_ in rep["wrong_shape"]] == ["skip_projection.bias"]
+    got = m.state_dict()
+    for k, v in sd.items():
+        if k != "skip_projection.bias":
+            np.testing.assert_array_equal(got[k].numpy(), v)
