@@ -72,6 +72,9 @@ typedef struct bvg_tuning {
   int32_t umma_pair;       /* default 1: wide convolutions (N tile >= 128) on the CTA-pair kernel (tcgen05.mma.cta_group::2);
                               0: single-CTA kernel, wide SPLIT layers then pack as stacked 128-column tiles;
                               2: single-tile SPLIT layers (C = 192) on the single-CTA kernel; 4: wide SPLIT layers keep 256 / 192-column tiles */
+  int32_t umma_pair_smem_kb; /* 0 = default; cap (KB) on the pair kernel's dynamic shared memory: fewer weight stages leave
+                              room for Activation1d CTAs of another stream on the same SM */
+  int32_t _reserved[3];
 } bvg_tuning;
 
 void bvg_tuning_defaults(bvg_tuning* t);

@@ -456,6 +456,10 @@ __global__ void __launch_bounds__(32 * NG) amp_mma_kernel(const __grid_constant_
 template <bool IN_BF16, int OUT_MODE, bool FAST_SIN, int NG>
 static cudaError_t launch_amp_mma(const AmpMmaParams& p, cudaStream_t st) {
   const long long blocks = (long long)p.B * p.n_ct * p.n_cg;
+  // same shared-memory carve-out as the convolution kernels (max shared): an SM hosts kernels of two streams at once
+  // only when they agree on the L1 / shared split
+  if (first_use_on_device(reinterpret_cast<const void*>(amp_mma_kernel<IN_BF16, OUT_MODE, FAST_SIN, NG>)))
+    cudaFuncSetAttribute(amp_mma_kernel<IN_BF16, OUT_MODE, FAST_SIN, NG>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   amp_mma_kernel<IN_BF16, OUT_MODE, FAST_SIN, NG><<<(unsigned)blocks, 32 * NG, 0, st>>>(p);
   return cudaGetLastError();
 }

@@ -519,12 +519,16 @@ int conv_pair_prepare(const bvg_conv_desc* d, PairLaunch* out) {
   p.a_stages = 2;
   if (3 * p.a_stage_bytes + 4 * (w->n_tile / 2) * 128 + UM_STAGING_BYTES + UM_BAR_BYTES + 1024 <= UM_SMEM_LIMIT) p.a_stages = 3;
   p.b_stage_bytes = (w->n_tile / 2) * 128;
-  int bs = (UM_SMEM_LIMIT - 1024 - UM_BAR_BYTES - UM_STAGING_BYTES - p.a_stages * p.a_stage_bytes) / p.b_stage_bytes;
+  int smem_cap = UM_SMEM_LIMIT;
+  const int cap_kb = tune_of(d->tune).umma_pair_smem_kb;
+  if (cap_kb > 0 && cap_kb * 1024 < smem_cap) smem_cap = cap_kb * 1024;
+  if (3 * p.a_stage_bytes + 4 * p.b_stage_bytes + UM_STAGING_BYTES + UM_BAR_BYTES + 1024 > smem_cap) p.a_stages = 2;
+  int bs = (smem_cap - 1024 - UM_BAR_BYTES - UM_STAGING_BYTES - p.a_stages * p.a_stage_bytes) / p.b_stage_bytes;
   if (bs > UM_MAX_B_STAGES) bs = UM_MAX_B_STAGES;
   BVG_REQUIRE(bs >= 2, "conv_pair: tile does not fit in shared memory (span %d, n_tile %d, planes %d)", max_span, w->n_tile, planes);
   p.b_stages = bs;
   out->smem = 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)bs * p.b_stage_bytes + UM_STAGING_BYTES + UM_BAR_BYTES;
-  if (out->smem < 120 * 1024) out->smem = 120 * 1024;  // one CTA per SM (each pair owns all 512 TMEM columns of its two SMs)
+  if (out->smem < 120 * 1024 && cap_kb == 0) out->smem = 120 * 1024;  // one CTA per SM (each pair owns all 512 TMEM columns of its two SMs)
 
   for (int pl = 0; pl < planes; ++pl) {
     void* xb = pl == 0 ? d->x.d_ptr : d->x.d_lo;
