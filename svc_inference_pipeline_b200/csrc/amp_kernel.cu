@@ -416,6 +416,10 @@ static cudaError_t launch_amp_p2_sin(const AmpParams& p, cudaStream_t st, bool a
       default: break;
     }
   }
+  if constexpr (!IN_BF16 && OUT_MODE == BVG_F32) {
+    // activation_post of the repo and v2 generators (F32 -> F32 at the last stage's 24 channels): 0.41 -> ~0.2 ms per forward
+    if (amp_ct_enable && p.C == 24) return launch_amp_p2_ct<IN_BF16, OUT_MODE, FAST_SIN, 24>(p, st);
+  }
   return launch_amp_p2_ct<IN_BF16, OUT_MODE, FAST_SIN, 0>(p, st);
 }
 
