@@ -385,6 +385,30 @@ def main():
                                    "bf16_path_log_mel_l1": log_mel_l1(ref_dev, yb[7:8]), "gate_bf16_log_mel_l1": 1e-2})
         model.set_precision(args.precision)
 
+    # ---- the two other checkpoint recipes of utils/synth.py against the reference on them (tests/golden/recipes.npz) ---
+    rec_path = os.path.join(ROOT, "tests", "golden", "recipes.npz")
+    if rank == 0 and world == 1 and "parity" in line and os.path.exists(rec_path) and not args.no_extra:
+        from svc_inference_pipeline_b200.utils.mel import log_mel_l1
+
+        rec = np.load(rec_path)
+        xr = torch.from_numpy(rec["mel"]).to(dev)
+        line["parity"]["recipes"] = {"what": "repo generator with the 'survey' (SURVEY 8d as written) and 'large_alpha' checkpoint recipes, 96 log-mel frames, vs the unmodified "
+                                             "reference's fp64 waveform; the fp32 gate (1e-4) must hold, the bf16 figures are reported (both nets amplify rounding: DESIGN.md section 5)"}
+        for recipe in ("survey", "large_alpha"):
+            mr = Generator(cfg.vocoder, precision="fp32")
+            mr.load_state_dict({k: torch.from_numpy(v) for k, v in synth.synthetic_state_dict(vcd, seed=0, recipe=recipe).items()})
+            mr = mr.to(dev).eval()
+            ref64 = rec[recipe + "_y_f64"]
+            y32 = mr(xr).cpu().numpy()
+            mr.set_precision("bf16")
+            yb = mr(xr)
+            line["parity"]["recipes"][recipe] = {
+                "fp32_path_max_abs_vs_ref_fp64": float(np.abs(y32 - ref64).max()), "reference_fp32_vs_its_fp64": float(np.abs(rec[recipe + "_y"] - ref64).max()),
+                "bf16_path_snr_db": snr_db(ref64, yb.cpu().numpy()),
+                "bf16_path_log_mel_l1": log_mel_l1(torch.from_numpy(ref64.astype(np.float32)).to(dev), yb)}
+            del mr
+        torch.cuda.empty_cache()
+
     if rank == 0:
         # configs[0] shape: one utterance of 379 frames (4.04 s) through synthesis_audios, eager and as a CUDA graph
         from svc_inference_pipeline_b200.modules.bigvgan_inference import synthesis_audios
