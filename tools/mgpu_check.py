@@ -36,13 +36,13 @@ if "--hour" in sys.argv:
     T = 337500  # one hour at 93.75 frames/s
     mel_h = torch.from_numpy(synth.synthetic_mel(1, 100, T, 79))[0].to(dev)
     for _ in range(2):
-        S.vocode_long_distributed(m, mel_h, 256, chunk_frames=938, batch_chunks=16)
+        S.vocode_long_distributed(m, mel_h, 256, chunk_frames=4096, batch_chunks=16)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    y = S.vocode_long_distributed(m, mel_h, 256, chunk_frames=938, batch_chunks=16)
+    y = S.vocode_long_distributed(m, mel_h, 256, chunk_frames=4096, batch_chunks=16)
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
