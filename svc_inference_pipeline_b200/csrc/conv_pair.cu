@@ -108,13 +108,13 @@ __device__ __forceinline__ void issue_wlo(uint32_t tmem_corr, uint64_t desc_hi, 
 
 // OUT / SBF / RES / ACC: the compile-time epilogue choices of conv_umma_kernel (N % 4 == 0 required: vec_ok)
 template <int OUT, bool SBF, bool RES, bool ACC>
-__global__ void __launch_bounds__(UM_THREADS, 1) conv_pair_kernel(const __grid_constant__ UmmaParams p) {
+__global__ void __launch_bounds__(PR_THREADS, 1) conv_pair_kernel(const __grid_constant__ UmmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
   const uint32_t b_base = a_base + p.a_stages * p.a_stage_bytes;
   const uint32_t stg_base = b_base + p.b_stages * p.b_stage_bytes;
-  const uint32_t bar_base = stg_base + UM_STAGING_BYTES;
+  const uint32_t bar_base = stg_base + PR_STAGING_BYTES;
   auto a_full = [&](int s) { return bar_base + 8u * s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (UM_MAX_A_STAGES + s); };
   auto b_full = [&](int s) { return bar_base + 8u * (2 * UM_MAX_A_STAGES + s); };
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_pair_kernel(const __grid_c
     }
     for (int s = 0; s < p.t_stages; ++s) {
       ptx::mbar_init(t_full(s), 1);                   // multicast commit
-      ptx::mbar_init(t_empty(s), 2 * UM_EPI_WARPS);  // (leader's copy is the one used) every epilogue warp of both CTAs
+      ptx::mbar_init(t_empty(s), 2 * PR_EPI_WARPS);  // (leader's copy is the one used) every epilogue warp of both CTAs
     }
     ptx::fence_barrier_init();
     ptx::fence_proxy_async();
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_pair_kernel(const __grid_c
       __syncwarp();
       if (++as == p.t_stages) { as = 0; ap ^= 1; }
     }
-  } else if (warp >= 4 && warp < 4 + UM_EPI_WARPS) {
+  } else if (warp >= 4 && warp < 4 + PR_EPI_WARPS) {
     // ================================ epilogue (both CTAs, own 128 rows) ================================
     const int e = warp - 4;
     const int q = e & 3;
@@ -517,17 +517,17 @@ int conv_pair_prepare(const bvg_conv_desc* d, PairLaunch* out) {
   p.a_plane_bytes = p.a_boxes * p.a_box_rows * 128;
   p.a_stage_bytes = p.a_plane_bytes * planes;
   p.a_stages = 2;
-  if (3 * p.a_stage_bytes + 4 * (w->n_tile / 2) * 128 + UM_STAGING_BYTES + UM_BAR_BYTES + 1024 <= UM_SMEM_LIMIT) p.a_stages = 3;
+  if (3 * p.a_stage_bytes + 4 * (w->n_tile / 2) * 128 + PR_STAGING_BYTES + UM_BAR_BYTES + 1024 <= UM_SMEM_LIMIT) p.a_stages = 3;
   p.b_stage_bytes = (w->n_tile / 2) * 128;
   int smem_cap = UM_SMEM_LIMIT;
   const int cap_kb = tune_of(d->tune).umma_pair_smem_kb;
   if (cap_kb > 0 && cap_kb * 1024 < smem_cap) smem_cap = cap_kb * 1024;
-  if (3 * p.a_stage_bytes + 4 * p.b_stage_bytes + UM_STAGING_BYTES + UM_BAR_BYTES + 1024 > smem_cap) p.a_stages = 2;
-  int bs = (smem_cap - 1024 - UM_BAR_BYTES - UM_STAGING_BYTES - p.a_stages * p.a_stage_bytes) / p.b_stage_bytes;
+  if (3 * p.a_stage_bytes + 4 * p.b_stage_bytes + PR_STAGING_BYTES + UM_BAR_BYTES + 1024 > smem_cap) p.a_stages = 2;
+  int bs = (smem_cap - 1024 - UM_BAR_BYTES - PR_STAGING_BYTES - p.a_stages * p.a_stage_bytes) / p.b_stage_bytes;
   if (bs > UM_MAX_B_STAGES) bs = UM_MAX_B_STAGES;
   BVG_REQUIRE(bs >= 2, "conv_pair: tile does not fit in shared memory (span %d, n_tile %d, planes %d)", max_span, w->n_tile, planes);
   p.b_stages = bs;
-  out->smem = 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)bs * p.b_stage_bytes + UM_STAGING_BYTES + UM_BAR_BYTES;
+  out->smem = 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)bs * p.b_stage_bytes + PR_STAGING_BYTES + UM_BAR_BYTES;
   if (out->smem < 120 * 1024 && cap_kb == 0) out->smem = 120 * 1024;  // one CTA per SM (each pair owns all 512 TMEM columns of its two SMs)
 
   for (int pl = 0; pl < planes; ++pl) {
@@ -582,7 +582,7 @@ int conv_pair_launch(const PairLaunch* l, cudaStream_t st) {
     BVG_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_LIMIT));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)l->grid, 1, 1);
-  cfg.blockDim = dim3(UM_THREADS, 1, 1);
+  cfg.blockDim = dim3(PR_THREADS, 1, 1);
   cfg.dynamicSmemBytes = l->smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

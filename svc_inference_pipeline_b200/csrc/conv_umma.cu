@@ -261,14 +261,15 @@ __device__ __forceinline__ void fused_amp_producer(const UmmaParams& p, uint32_t
 //   RES  : a residual is added            ACC : a running sum is added (and maybe divided)
 //   GEN  : generic fallback -- every choice read from the descriptor at run time, ragged N allowed
 template <int OUT, bool SBF, bool RES, bool ACC, bool GEN, bool FUSED = false>
-__global__ void __launch_bounds__(FUSED ? UM_THREADS_FUSED : UM_THREADS, 1) conv_umma_kernel(const __grid_constant__ UmmaParams p) {
+__global__ void __launch_bounds__(FUSED ? UM_THREADS_FUSED : 128 + 32 * UM_EPI_WARPS_MAX, 1) conv_umma_kernel(const __grid_constant__ UmmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve-up: [A stages][B stages][epilogue staging][barriers][tmem ptr]; base rounded up to 1024 B
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
   const uint32_t b_base = a_base + p.a_stages * p.a_stage_bytes;
   const uint32_t stg_base = b_base + p.b_stages * p.b_stage_bytes;
-  const uint32_t bar_base = stg_base + UM_STAGING_BYTES;
+  const int n_epi = FUSED ? UM_EPI_WARPS : p.epi_warps;
+  const uint32_t bar_base = stg_base + (uint32_t)n_epi * 2048u;  // 32 rows x 16 fp32 of staging per epilogue warp
   auto a_full = [&](int s) { return bar_base + 8u * s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (UM_MAX_A_STAGES + s); };
   auto b_full = [&](int s) { return bar_base + 8u * (2 * UM_MAX_A_STAGES + s); };
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(FUSED ? UM_THREADS_FUSED : UM_THREADS, 1) conv
     }
     for (int s = 0; s < p.t_stages; ++s) {
       ptx::mbar_init(t_full(s), 1);
-      ptx::mbar_init(t_empty(s), UM_EPI_WARPS);  // one arrive per epilogue warp
+      ptx::mbar_init(t_empty(s), n_epi);  // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
     ptx::fence_proxy_async();
@@ -443,7 +444,7 @@ __global__ void __launch_bounds__(FUSED ? UM_THREADS_FUSED : UM_THREADS, 1) conv
         if (++as == p.t_stages) { as = 0; ap ^= 1; }
       }
     }
-  } else if (warp >= 4 && warp < 4 + UM_EPI_WARPS) {
+  } else if (warp >= 4 && warp < 4 + n_epi) {
     // ================================ epilogue ====================================
     // Warp e owns TMEM lane quarter q = e % 4 (rows 32q..32q+31 of every M block) and every second
     // (M block, 16-column chunk) work item.  Each chunk goes TMEM -> registers (thread = row) ->
@@ -457,7 +458,8 @@ __global__ void __launch_bounds__(FUSED ? UM_THREADS_FUSED : UM_THREADS, 1) conv
     const int n_items = p.mb * n_chunks;
     const int rrow = lane >> 2;   // row within an 8-row group after the transposition
     const int g = lane & 3;       // 16-byte granule (4 columns) within the 16-column chunk
-    const int n_my = (n_items - grp + 1) >> 1;  // items grp, grp+2, ...
+    const int NGRP = n_epi >> 2;  // warps per lane quarter
+    const int n_my = n_items > grp ? (n_items - grp + NGRP - 1) / NGRP : 0;  // items grp, grp + NGRP, ...
     const bool has_res = GEN ? (p.epi.res != nullptr) : RES;
     const bool has_acc = GEN ? (p.epi.acc != nullptr) : ACC;
     const bool res_bf = GEN ? (p.epi.res_dtype != BVG_F32) : SBF;
@@ -480,7 +482,7 @@ __global__ void __launch_bounds__(FUSED ? UM_THREADS_FUSED : UM_THREADS, 1) conv
         int it_mbi[2], it_c0[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          const int it = grp + 2 * (pb2 + u);
+          const int it = grp + NGRP * (pb2 + u);
           const int mbi = it / n_chunks;
           it_mbi[u] = mbi;
           it_c0[u] = (it - mbi * n_chunks) << 4;
@@ -690,14 +692,14 @@ static const int kBarBytes = 8 * (2 * UM_MAX_A_STAGES + 2 * UM_MAX_B_STAGES + 2 
 // shared-memory plan for a given number of M blocks: picks the taps per weight stage (narrow N
 // tiles group several taps into one TMA box / one barrier round trip) and returns the number of
 // weight stages that fit
-static int plan_smem(int umma_tap_group, int mb, int a_stages, int max_span, int planes, int n_tile, int max_taps, int* box_rows, int* boxes, int* tap_group) {
+static int plan_smem(int staging_bytes, int umma_tap_group, int mb, int a_stages, int max_span, int planes, int n_tile, int max_taps, int* box_rows, int* boxes, int* tap_group) {
   const int rows = mb * UM_BM + max_span;
   const int nb = (rows + 255) / 256;
   const int br = (((rows + nb - 1) / nb) + 7) / 8 * 8;
   *box_rows = br;
   *boxes = nb;
   const int a_stage = nb * br * 128 * planes;
-  const int avail = UM_SMEM_LIMIT - 1024 - kBarBytes - UM_STAGING_BYTES - a_stages * a_stage;
+  const int avail = UM_SMEM_LIMIT - 1024 - kBarBytes - staging_bytes - a_stages * a_stage;
   if (avail <= 0) return 0;
   int g = umma_tap_group > 0 ? umma_tap_group : 24 * 1024 / (n_tile * 128);  // ~24 KB per stage
   if (g > 256 / n_tile) g = 256 / n_tile;                                      // TMA box <= 256 rows
@@ -741,6 +743,9 @@ int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out) {
             umma_a_stages = T.umma_a_stages;
   UmmaParams& p = out->p;
   memset(&p, 0, sizeof(p));
+  // four epilogue warps per TMEM lane quarter for bf16 operands (conv_umma.cuh), two otherwise and with the fused producer
+  p.epi_warps = (planes == 1 && !fused) ? UM_EPI_WARPS_MAX : UM_EPI_WARPS;
+  const int staging_bytes = p.epi_warps * 2048;
   int rc = fill_epilogue(d, p.epi);
   if (rc != BVG_OK) return rc;
   p.planes = planes;
@@ -786,7 +791,7 @@ int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out) {
                                  (umma_wide_mb2 > 0 || (umma_wide_mb2 == 0 && planes == 2 && p.col_stride == 256));
     const bool tmem_ok = cand * p.col_stride * 2 <= 512 || (cand == 1) || single_stage_ok;
     if (!tmem_ok) continue;
-    if (plan_smem(umma_tap_group, cand, 2, max_span, planes, w_rows, max_taps, &br, &nb, &tg) < (cand == 1 ? 2 : 3)) continue;
+    if (plan_smem(staging_bytes, umma_tap_group, cand, 2, max_span, planes, w_rows, max_taps, &br, &nb, &tg) < (cand == 1 ? 2 : 3)) continue;
     const long long tiles = (long long)d->B * ceil_div(d->L, cand * UM_BM) * w->n_tiles;
     if (cand > 1 && tiles < 2ll * sms) continue;
     mb = cand;
@@ -806,24 +811,24 @@ int conv_umma_prepare(const bvg_conv_desc* d, UmmaLaunch* out) {
   int a_stages = 2;
   for (int cand = UM_MAX_A_STAGES; cand > 2; --cand) {
     int br, nb, tg;
-    if (umma_a_stages == -1 && p.n_cb <= 2 && plan_smem(umma_tap_group, mb, cand, max_span, planes, w_rows, max_taps, &br, &nb, &tg) >= 3) {
+    if (umma_a_stages == -1 && p.n_cb <= 2 && plan_smem(staging_bytes, umma_tap_group, mb, cand, max_span, planes, w_rows, max_taps, &br, &nb, &tg) >= 3) {
       a_stages = cand;
       break;
     }
   }
   if (fused) {  // the producer of tile i+1 runs under the MMAs of tile i: one spare stage when it fits
     int br, nb, tg;
-    if (plan_smem(umma_tap_group, mb, 3, max_span, planes, w_rows, max_taps, &br, &nb, &tg) >= 3) a_stages = 3;
+    if (plan_smem(staging_bytes, umma_tap_group, mb, 3, max_span, planes, w_rows, max_taps, &br, &nb, &tg) >= 3) a_stages = 3;
   }
   if (umma_a_stages >= 2 && umma_a_stages <= UM_MAX_A_STAGES) a_stages = umma_a_stages;
   p.a_stages = a_stages;
-  const int bs = plan_smem(umma_tap_group, mb, a_stages, max_span, planes, w_rows, max_taps, &p.a_box_rows, &p.a_boxes, &p.tap_group);
+  const int bs = plan_smem(staging_bytes, umma_tap_group, mb, a_stages, max_span, planes, w_rows, max_taps, &p.a_box_rows, &p.a_boxes, &p.tap_group);
   BVG_REQUIRE(bs >= 2, "conv_umma: tile does not fit in shared memory (mb %d, span %d, n_tile %d, planes %d)", mb, max_span, w->n_tile, planes);
   p.b_stages = bs;
   p.a_plane_bytes = p.a_boxes * p.a_box_rows * 128;
   p.a_stage_bytes = p.a_plane_bytes * planes;
   p.b_stage_bytes = p.tap_group * w_rows * 128;
-  size_t smem = 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)bs * p.b_stage_bytes + UM_STAGING_BYTES + kBarBytes;
+  size_t smem = 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)bs * p.b_stage_bytes + (size_t)staging_bytes + kBarBytes;
   // keep one CTA per SM (each allocates all 512 TMEM columns): ask for more than half the SM's smem
   if (smem < 120 * 1024) smem = 120 * 1024;
   BVG_REQUIRE(smem <= (size_t)UM_SMEM_LIMIT, "conv_umma: shared memory plan exceeds the limit");
@@ -905,7 +910,7 @@ int conv_umma_launch(const UmmaLaunch* l, cudaStream_t st) {
   // opt in to > 48 KB of dynamic shared memory once per (device, specialisation): the attribute is per device
   if (first_use_on_device(reinterpret_cast<const void*>(k)))
     BVG_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_LIMIT));
-  k<<<l->grid, l->p.f_x ? UM_THREADS_FUSED : UM_THREADS, l->smem, st>>>(l->p);
+  k<<<l->grid, l->p.f_x ? UM_THREADS_FUSED : 128 + 32 * l->p.epi_warps, l->smem, st>>>(l->p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "conv_umma_kernel launch");
   return BVG_OK;

@@ -10,7 +10,14 @@ namespace bvg {
 
 constexpr int UM_BM = 128;          // rows per M block (TMEM lanes)
 constexpr int UM_KB = 64;           // channels per K slice (one 128-byte swizzle row of bf16)
-constexpr int UM_EPI_WARPS = 8;     // two warps per TMEM lane quarter
+constexpr int UM_EPI_WARPS = 8;      // epilogue warps of the single-CTA kernel (two per TMEM lane quarter) ...
+constexpr int UM_EPI_WARPS_MAX = 16; // ... or four per quarter for bf16 operands (UmmaParams.epi_warps): the narrow layers' epilogue is
+                                     // a latency-bound stream of global loads / stores, and with one MMA pass per product it is what
+                                     // bounds them (measured per forward, bf16 path: C = 96 / 48 / 24 classes 3.90 / 3.22 / 3.57 ->
+                                     // 3.36 / 2.79 / 3.13 ms; with the three passes of the fp32 path it changes nothing)
+constexpr int PR_EPI_WARPS = 8;              // epilogue warps per CTA of the pair kernel
+constexpr int PR_THREADS = 128 + 32 * PR_EPI_WARPS;
+constexpr int PR_STAGING_BYTES = PR_EPI_WARPS * 32 * 64;
 constexpr int UM_THREADS = 128 + 32 * UM_EPI_WARPS;
 constexpr int UM_AMP_WARPS = 8;      // fused mode: Activation1d producer warps after the epilogue warps
 constexpr int UM_THREADS_FUSED = UM_THREADS + 32 * UM_AMP_WARPS;
@@ -45,6 +52,7 @@ struct UmmaParams {
   int a_plane_bytes;
   int b_stage_bytes;
   int vec_ok;
+  int epi_warps;        // epilogue warps of this launch (single-CTA kernel: 8 or 16; block = 128 + 32 * epi_warps threads)
   int n_taps[BVG_MAX_NTILES];
   int min_shift[BVG_MAX_NTILES];
   int shift[BVG_MAX_NTILES][BVG_MAX_TAPS];
