@@ -456,6 +456,26 @@ def main():
                 a1.record()
                 torch.cuda.synchronize(dev)
                 dstep[f"{prec}_b{b_}x{l_}_ms"] = a0.elapsed_time(a1) / 20
+        # the sampler that drives it (modules/diffsvcrepo_inference.py::svc_model_inference, the call infer.py:79 makes): the
+        # reference's 1000-step schedule on one utterance of config 1's length, host wall clock, result copied to the host
+        from svc_inference_pipeline_b200.modules.diffsvcrepo_inference import svc_model_inference
+
+        sched = np.linspace(1e-4, 0.02, 1000).tolist()
+        scfg = JsonHParams(mapper=JsonHParams(noise_schedule=sched))
+        cond_fn = lambda batch: batch["cond"]
+        batch = {"y": torch.zeros(1, 379, 100, device=dev), "cond": torch.randn(1, 379, 384, device=dev)}
+        samp = {"what": "svc_model_inference([cond, DiffSVC], batch, cfg) on one utterance of 379 frames, 1000 p_sample steps (default) / 100 PLMS steps "
+                        "(fast_inference, speedup 10): seconds per utterance, host wall clock incl. the copy of the mel to the host"}
+        for prec in ("fp32", "bf16"):
+            dm.set_precision(prec)
+            for fast in (False, True):
+                svc_model_inference([cond_fn, dm], batch, JsonHParams(mapper=JsonHParams(noise_schedule=sched[:20])), fast_inference=fast, speedup=10)  # graphs
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                y = svc_model_inference([cond_fn, dm], batch, scfg, fast_inference=fast, speedup=10).cpu()
+                samp[f"{prec}_{'plms100' if fast else 'ddpm1000'}_s"] = time.perf_counter() - t0
+                samp[f"{prec}_{'plms100' if fast else 'ddpm1000'}_finite"] = bool(torch.isfinite(y).all())
+        dstep["sampler"] = samp
         line["diffsvc_step"] = dstep
         del dm
         torch.cuda.empty_cache()

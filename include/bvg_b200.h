@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BVG_ABI_VERSION 4  /* 2: bvg_conv_geom.fold, bvg_conv_desc.pre_amp; 3: bvg_stitch_fwd; 4: bvg_tuning in the descriptors (bvg_set_tuning removed), bvg_logmel_fwd, bvg_rowop_fwd, bvg_diffembed_fwd, bvg_conv_desc.relu */
+#define BVG_ABI_VERSION 5  /* 2: bvg_conv_geom.fold, bvg_conv_desc.pre_amp; 3: bvg_stitch_fwd; 4: bvg_tuning in the descriptors (bvg_set_tuning removed), bvg_logmel_fwd, bvg_rowop_fwd, bvg_diffembed_fwd, bvg_conv_desc.relu; 5: bvg_sample_fwd, bvg_program_set_pdl */
 
 enum bvg_status {
   BVG_OK = 0,
@@ -324,6 +324,45 @@ typedef struct bvg_diffembed_desc {
 
 int bvg_diffembed_fwd(const bvg_diffembed_desc* d, void* stream);
 
+/* One update of the diffusion sampler that drives the denoiser (modules/diffsvcrepo_inference.py): everything the
+ * reference does between two denoiser calls, as one elementwise launch over the sample x[B, L, n_mel] (the memory
+ * of the reference's x[B, 1, n_mel, T] transposed, i.e. the layout the denoiser reads).  Every product, sum and
+ * quotient is rounded separately in fp32 in the reference's order (no contraction).
+ *   BVG_SAMPLE_DDPM (p_sample :88-97 = predict_start_from_noise :32-36, clamp :76-77, q_posterior :39-50):
+ *       x0 = clamp(sqrt_recip[t] x - sqrt_recipm1[t] eps, -1, 1)               (clamp iff clip)
+ *       x' = (coef1[t] x0 + coef2[t] x) + [t != 0] exp(0.5 logvar[t]) noise
+ *     noise is the reference's torch.randn(x.shape): [B, n_mel, L]; the five tables have n_steps entries.
+ *   BVG_SAMPLE_PLMS (p_sample_plms :100-150): e' = the linear multistep combination of eps and the history
+ *       combine 0: eps | 1: (h0 + eps) / 2 | 2: (3 eps - h0) / 2 | 3: (23 eps - 16 h0 + 5 h1) / 12
+ *             | 4: (55 eps - 59 h0 + 37 h1 - 9 h2) / 24        (h0 = the most recent earlier prediction)
+ *       x' = x + (a_prev - a_t) ((1 / (sqrt a_t (sqrt a_t + sqrt a_prev))) x
+ *                 - (1 / (sqrt a_t (sqrt((1 - a_prev) a_t) + sqrt((1 - a_t) a_prev)))) e')       (get_x_pred :105-121)
+ *     with a_t = alphas_cumprod[t], a_prev = alphas_cumprod[max(t - interval, 0)].
+ * d_x_out may alias d_x.  d_eps_save (optional) receives a copy of eps (the sampler's noise_list entry). */
+enum bvg_sample_mode { BVG_SAMPLE_DDPM = 0, BVG_SAMPLE_PLMS = 1 };
+
+typedef struct bvg_sample_desc {
+  int32_t mode; /* bvg_sample_mode */
+  int32_t clip; /* DDPM: clamp the predicted x0 to [-1, 1] (clip_denoised) */
+  const float* d_x;
+  float* d_x_out;
+  const float* d_eps;
+  const float* d_noise;  /* DDPM: [B, n_mel, L] */
+  const int32_t* d_step; /* [B] */
+  const float* d_sqrt_recip;   /* DDPM tables, [n_steps] each */
+  const float* d_sqrt_recipm1;
+  const float* d_coef1;
+  const float* d_coef2;
+  const float* d_logvar;
+  const float* d_alphas_cumprod; /* PLMS, [n_steps] */
+  const float* d_hist[3];        /* PLMS: earlier predictions, most recent first */
+  float* d_eps_save;
+  int32_t interval, combine;
+  int32_t B, L, n_mel, n_steps;
+} bvg_sample_desc;
+
+int bvg_sample_fwd(const bvg_sample_desc* d, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Log-mel front end (replaces mel_spectrogram, utils/mel.py:130-174, which the
  * reference runs with torch.stft + a librosa mel basis on the host: reflect pad (n_fft - hop) / 2, frames
@@ -353,8 +392,8 @@ int bvg_convert(const bvg_tensor* src, const bvg_tensor* dst, size_t n_elems, vo
  * Programs: a whole Generator.forward (modules/bigvgan.py:600-622) as one pre-validated launch
  * list, so the per-call host work is one C call (and the list can be captured in a CUDA graph).
  * ------------------------------------------------------------------------------------------ */
-enum bvg_op_kind { BVG_OP_PACK = 0, BVG_OP_AMP = 1, BVG_OP_CONV = 2, BVG_OP_POST = 3, BVG_OP_ROWOP = 4, BVG_OP_DIFFEMBED = 5 };
-#define BVG_N_OP_KINDS 6
+enum bvg_op_kind { BVG_OP_PACK = 0, BVG_OP_AMP = 1, BVG_OP_CONV = 2, BVG_OP_POST = 3, BVG_OP_ROWOP = 4, BVG_OP_DIFFEMBED = 5, BVG_OP_SAMPLE = 6 };
+#define BVG_N_OP_KINDS 7
 
 typedef struct bvg_op {
   int32_t kind; /* bvg_op_kind */
@@ -366,6 +405,7 @@ typedef struct bvg_op {
     bvg_post_desc post;
     bvg_rowop_desc rowop;
     bvg_diffembed_desc diffembed;
+    bvg_sample_desc sample;
   } u;
 } bvg_op;
 
@@ -381,6 +421,12 @@ int bvg_program_run_timed(bvg_program* p, void* stream, float* ms_by_kind, int32
  * order; launching the ops alternately lets one half-batch's tensor-core convolutions (one persistent CTA per
  * SM, almost no issue slots) share the SMs with the other half-batch's FFMA-bound Activation1d kernels. */
 int bvg_program_run_interleaved(bvg_program* const* progs, void* const* streams, int32_t n);
+/* Chain the program's launches with programmatic dependent launch: every kernel is launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization, signals `griddepcontrol.launch_dependents` on entry and
+ * executes `griddepcontrol.wait` after its set-up and before its first global access, so that launch latency and
+ * prologue (barrier init, TMEM allocation, tensor-map prefetch) of launch i + 1 overlap launch i.  Pays on
+ * latency-bound programs (one utterance; a DiffSVC step); off by default. */
+int bvg_program_set_pdl(bvg_program* p, int on);
 int bvg_program_num_launches(const bvg_program* p);
 void bvg_program_destroy(bvg_program* p);
 

@@ -35,7 +35,7 @@ def denoiser_forward(sd: dict, cfg, mel_spec: torch.Tensor, conditioner: torch.T
     nl = int(_get(cfg, "residual_layer_num"))
     cycle = int(_get(cfg, "dilation_cycle_length"))
     ks = int(_get(cfg, "residual_kernel_size"))
-    table = build_embedding(int(_get(cfg, "noise_schedule_factors")[2])).to(dt)
+    table = build_embedding(int(_get(cfg, "noise_schedule_factors")[2])).to(device=mel_spec.device, dtype=dt)
     # SpectrogramPreprocessor (:118-128)
     x = F.relu(F.conv1d(mel_spec.transpose(1, 2), w("mel_preprocess.projection.weight"), w("mel_preprocess.projection.bias")))
     # StepEncoder, integer steps (:79-91)

@@ -14,11 +14,12 @@ LIB_PATH = os.environ.get("BVG_B200_LIB") or os.path.join(_HERE, "libbvg_b200.so
 
 F32, BF16, SPLIT = 0, 1, 2
 SIMT, UMMA = 0, 1
-OP_PACK, OP_AMP, OP_CONV, OP_POST, OP_ROWOP, OP_DIFFEMBED = 0, 1, 2, 3, 4, 5
-N_OP_KINDS = 6
+OP_PACK, OP_AMP, OP_CONV, OP_POST, OP_ROWOP, OP_DIFFEMBED, OP_SAMPLE = 0, 1, 2, 3, 4, 5, 6
+N_OP_KINDS = 7
 ROW_ADDVEC, ROW_GATE, ROW_SCALE = 0, 1, 2
+SAMPLE_DDPM, SAMPLE_PLMS = 0, 1
 MAX_TAPS, MAX_NTILES = 16, 32
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class BvgError(RuntimeError):
@@ -199,8 +200,14 @@ class DiffEmbedDesc(C.Structure):
         (n, C.c_int32) for n in ("B", "emb", "fc", "C", "n_layers", "max_steps")] + [("d_step_f", C.c_void_p)]
 
 
+class SampleDesc(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("clip", C.c_int32)] + [
+        (n, C.c_void_p) for n in ("d_x", "d_x_out", "d_eps", "d_noise", "d_step", "d_sqrt_recip", "d_sqrt_recipm1", "d_coef1", "d_coef2", "d_logvar", "d_alphas_cumprod")] + [
+        ("d_hist", C.c_void_p * 3), ("d_eps_save", C.c_void_p)] + [(n, C.c_int32) for n in ("interval", "combine", "B", "L", "n_mel", "n_steps")]
+
+
 class _OpUnion(C.Union):
-    _fields_ = [("pack", PackDesc), ("amp", AmpDesc), ("conv", ConvDesc), ("post", PostDesc), ("rowop", RowopDesc), ("diffembed", DiffEmbedDesc)]
+    _fields_ = [("pack", PackDesc), ("amp", AmpDesc), ("conv", ConvDesc), ("post", PostDesc), ("rowop", RowopDesc), ("diffembed", DiffEmbedDesc), ("sample", SampleDesc)]
 
 
 class Op(C.Structure):
@@ -229,12 +236,14 @@ EXPORTS = [
     "bvg_logmel_fwd",
     "bvg_rowop_fwd",
     "bvg_diffembed_fwd",
+    "bvg_sample_fwd",
     "bvg_convert",
     "bvg_program_create",
     "bvg_program_run",
     "bvg_program_run_interleaved",
     "bvg_program_run_timed",
     "bvg_tuning_defaults",
+    "bvg_program_set_pdl",
     "bvg_program_num_launches",
     "bvg_program_destroy",
 ]
@@ -267,6 +276,7 @@ def lib():
         "bvg_logmel_fwd": [C.POINTER(LogmelDesc), C.c_void_p],
         "bvg_rowop_fwd": [C.POINTER(RowopDesc), C.c_void_p],
         "bvg_diffembed_fwd": [C.POINTER(DiffEmbedDesc), C.c_void_p],
+        "bvg_sample_fwd": [C.POINTER(SampleDesc), C.c_void_p],
         "bvg_convert": [C.POINTER(Tensor), C.POINTER(Tensor), C.c_size_t, C.c_void_p],
         "bvg_conv_geometry": [C.POINTER(ConvGeom), C.POINTER(ConvWeights)],
         "bvg_conv_pack_bytes": [C.POINTER(ConvGeom), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)],
@@ -276,6 +286,7 @@ def lib():
         "bvg_program_run": [C.c_void_p, C.c_void_p],
         "bvg_program_run_interleaved": [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32],
         "bvg_program_run_timed": [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_float)],
+        "bvg_program_set_pdl": [C.c_void_p, C.c_int],
         "bvg_program_num_launches": [C.c_void_p],
         "bvg_program_destroy": [C.c_void_p],
     }.items():

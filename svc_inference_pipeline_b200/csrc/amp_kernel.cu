@@ -167,6 +167,8 @@ __device__ __forceinline__ void amp_block6(const AmpParams& p, const float (&xa)
 
 template <bool IN_BF16, int OUT_MODE, int VEC, bool FAST_SIN>
 __global__ void __launch_bounds__(128) amp_kernel(const __grid_constant__ AmpParams p) {
+  pdl_trigger();  // programmatic dependent launch (common.cuh): no global access before the wait
+  pdl_wait();
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= p.total_threads) return;
   const int cg = (int)(tid % p.CG);
@@ -325,6 +327,8 @@ __device__ __forceinline__ void amp_block6_p2(const AmpParams& p, const P2 (&xa)
 // ties below, 72 and 64 spill heavily.  The bf16 variants spill at 64 (2.4x slower).
 template <bool IN_BF16, int OUT_MODE, bool FAST_SIN, int CT>
 __global__ void __launch_bounds__(128, 6) amp_kernel_p2(const __grid_constant__ AmpParams p) {
+  pdl_trigger();  // programmatic dependent launch (common.cuh): no global access before the wait
+  pdl_wait();
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= p.total_threads) return;
   const int Cc = CT ? CT : p.C;
@@ -396,8 +400,7 @@ static cudaError_t launch_amp_p2_ct(const AmpParams& p, cudaStream_t st) {
   // two streams at once when they agree on the L1 / shared split, and this kernel streams through L2 anyway.
   if (first_use_on_device(reinterpret_cast<const void*>(amp_kernel_p2<IN_BF16, OUT_MODE, FAST_SIN, CT>)))
     cudaFuncSetAttribute(amp_kernel_p2<IN_BF16, OUT_MODE, FAST_SIN, CT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  amp_kernel_p2<IN_BF16, OUT_MODE, FAST_SIN, CT><<<(unsigned)blocks, threads, 0, st>>>(p);
-  return cudaGetLastError();
+  return launch_k(amp_kernel_p2<IN_BF16, OUT_MODE, FAST_SIN, CT>, dim3((unsigned)blocks), dim3(threads), 0, st, p);
 }
 
 
@@ -443,8 +446,7 @@ template <bool IN_BF16, int OUT_MODE, int VEC, bool FAST_SIN>
 static cudaError_t launch_amp(const AmpParams& p, cudaStream_t st) {
   const int threads = 128;
   const long long blocks = ceil_div_ll(p.total_threads, threads);
-  amp_kernel<IN_BF16, OUT_MODE, VEC, FAST_SIN><<<(unsigned)blocks, threads, 0, st>>>(p);
-  return cudaGetLastError();
+  return launch_k(amp_kernel<IN_BF16, OUT_MODE, VEC, FAST_SIN>, dim3((unsigned)blocks), dim3(threads), 0, st, p);
 }
 
 template <bool IN_BF16, int OUT_MODE, int VEC>

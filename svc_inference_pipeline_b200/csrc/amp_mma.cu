@@ -59,6 +59,8 @@ __global__ void __launch_bounds__(32 * NG) amp_mma_kernel(const __grid_constant_
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int g = tid >> 5;
+  pdl_trigger();  // programmatic dependent launch (common.cuh): no global access before the wait
+  pdl_wait();
 
   const int cgi = blockIdx.x % p.n_cg;
   const int rest = blockIdx.x / p.n_cg;
@@ -460,8 +462,7 @@ static cudaError_t launch_amp_mma(const AmpMmaParams& p, cudaStream_t st) {
   // only when they agree on the L1 / shared split
   if (first_use_on_device(reinterpret_cast<const void*>(amp_mma_kernel<IN_BF16, OUT_MODE, FAST_SIN, NG>)))
     cudaFuncSetAttribute(amp_mma_kernel<IN_BF16, OUT_MODE, FAST_SIN, NG>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  amp_mma_kernel<IN_BF16, OUT_MODE, FAST_SIN, NG><<<(unsigned)blocks, 32 * NG, 0, st>>>(p);
-  return cudaGetLastError();
+  return launch_k(amp_mma_kernel<IN_BF16, OUT_MODE, FAST_SIN, NG>, dim3((unsigned)blocks), dim3(32 * NG), 0, st, p);
 }
 
 template <bool IN_BF16, int OUT_MODE, bool FAST_SIN>

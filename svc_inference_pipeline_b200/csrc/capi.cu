@@ -12,6 +12,8 @@ namespace bvg {
 
 // ---- error plumbing -------------------------------------------------------------------------
 static thread_local char g_err[1024] = "";
+static thread_local bool g_pdl = false;
+bool& pdl_mode() { return g_pdl; }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -45,6 +47,7 @@ int stitch_forward(const bvg_stitch_desc* d, cudaStream_t st);
 int logmel_forward(const bvg_logmel_desc* d, cudaStream_t st);
 int rowop_forward(const bvg_rowop_desc* d, cudaStream_t st);
 int diffembed_forward(const bvg_diffembed_desc* d, cudaStream_t st);
+int sample_forward(const bvg_sample_desc* d, cudaStream_t st);
 int convert(const bvg_tensor* src, const bvg_tensor* dst, size_t n, cudaStream_t st);
 int conv_geometry(const bvg_conv_geom* g, bvg_conv_weights* w);
 size_t conv_plane_elems(const bvg_conv_weights* w);
@@ -83,6 +86,7 @@ struct bvg_program {
   std::vector<void*> umma;  // UmmaLaunch* per op (nullptr for the others)
   std::vector<void*> pair;  // PairLaunch* per op: convolutions that run on the CTA-pair kernel
   int launches = 0;
+  bool pdl = false;  // bvg_program_set_pdl: chain the launches with programmatic dependent launch (common.cuh)
   ~bvg_program() {
     for (auto* w : owned_weights) delete w;
     for (auto* t : owned_tunings) delete t;
@@ -121,6 +125,7 @@ int bvg_pack_mel(const bvg_pack_desc* d, void* stream) { return bvg::pack_mel(d,
 int bvg_tail_fwd(const bvg_tail_desc* d, void* stream) { return bvg::tail_forward(d, (cudaStream_t)stream); }
 int bvg_rowop_fwd(const bvg_rowop_desc* d, void* stream) { return bvg::rowop_forward(d, (cudaStream_t)stream); }
 int bvg_diffembed_fwd(const bvg_diffembed_desc* d, void* stream) { return bvg::diffembed_forward(d, (cudaStream_t)stream); }
+int bvg_sample_fwd(const bvg_sample_desc* d, void* stream) { return bvg::sample_forward(d, (cudaStream_t)stream); }
 int bvg_logmel_fwd(const bvg_logmel_desc* d, void* stream) { return bvg::logmel_forward(d, (cudaStream_t)stream); }
 int bvg_stitch_fwd(const bvg_stitch_desc* d, void* stream) { return bvg::stitch_forward(d, (cudaStream_t)stream); }
 int bvg_convert(const bvg_tensor* src, const bvg_tensor* dst, size_t n, void* stream) {
@@ -204,7 +209,7 @@ int bvg_program_create(const bvg_op* ops, int32_t n_ops, bvg_program** out) {
           return rc;
         }
       }
-    } else if (op.kind != BVG_OP_PACK && op.kind != BVG_OP_AMP && op.kind != BVG_OP_POST && op.kind != BVG_OP_ROWOP && op.kind != BVG_OP_DIFFEMBED) {
+    } else if (op.kind != BVG_OP_PACK && op.kind != BVG_OP_AMP && op.kind != BVG_OP_POST && op.kind != BVG_OP_ROWOP && op.kind != BVG_OP_DIFFEMBED && op.kind != BVG_OP_SAMPLE) {
       bvg::set_error("program_create: op %d has unknown kind %d", i, op.kind);
       delete p;
       return BVG_EINVAL;
@@ -217,6 +222,7 @@ int bvg_program_create(const bvg_op* ops, int32_t n_ops, bvg_program** out) {
 
 static int run_one(bvg_program* p, size_t i, cudaStream_t st) {
   const bvg_op& op = p->ops[i];
+  bvg::PdlScope scope(p->pdl);
   switch (op.kind) {
     case BVG_OP_PACK: return bvg::pack_mel(&op.u.pack, st);
     case BVG_OP_AMP: return bvg::amp_forward(&op.u.amp, st);
@@ -226,6 +232,7 @@ static int run_one(bvg_program* p, size_t i, cudaStream_t st) {
     case BVG_OP_POST: return bvg::post_forward(&op.u.post, st);
     case BVG_OP_ROWOP: return bvg::rowop_forward(&op.u.rowop, st);
     case BVG_OP_DIFFEMBED: return bvg::diffembed_forward(&op.u.diffembed, st);
+    case BVG_OP_SAMPLE: return bvg::sample_forward(&op.u.sample, st);
     default: return BVG_EINVAL;
   }
 }
@@ -240,6 +247,15 @@ int bvg_program_run(bvg_program* p, void* stream) {
     int rc = run_one(p, i, st);
     if (rc != BVG_OK) return rc;
   }
+  return BVG_OK;
+}
+
+int bvg_program_set_pdl(bvg_program* p, int on) {
+  if (!p) {
+    bvg::set_error("program_set_pdl: null program");
+    return BVG_EINVAL;
+  }
+  p->pdl = on != 0;
   return BVG_OK;
 }
 

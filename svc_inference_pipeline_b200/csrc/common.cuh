@@ -7,6 +7,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <utility>
 
 #include "../../include/bvg_b200.h"
 
@@ -46,6 +47,40 @@ inline bvg_tuning default_tuning() {
   return t;
 }
 inline bvg_tuning tune_of(const bvg_tuning* t) { return t ? *t : default_tuning(); }
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------
+// A program (bvg_program) is a fixed chain of dependent launches, many of them a few microseconds long (a DiffSVC
+// step: 106 launches, 1.8 ms).  With the programmaticStreamSerialization launch attribute a kernel's CTAs may be
+// scheduled while its predecessor still runs: every kernel of the chain fires `griddepcontrol.launch_dependents` on
+// entry, sets itself up (barriers, TMEM, tensor-map prefetch, index math), and executes `griddepcontrol.wait` --
+// which returns once the predecessor grid has completed and its writes are visible -- before its first access to
+// global memory.  Launch latency and prologue then overlap the predecessor instead of following it.  The attribute
+// is only ever given to kernels that contain the wait; `pdl_mode()` is thread-local, set by bvg_program_run for the
+// duration of the call when the program asks for it (bvg_program_set_pdl) and false everywhere else.
+bool& pdl_mode();
+struct PdlScope {
+  bool prev;
+  explicit PdlScope(bool on) : prev(pdl_mode()) { pdl_mode() = on; }
+  ~PdlScope() { pdl_mode() = prev; }
+};
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_mode() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }

@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) conv_pair_kernel(const __grid_c
   const uint32_t rank = ptx2::cluster_ctarank();
   const bool leader = rank == 0;
   const long long pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  pdl_trigger();  // the next launch of the chain may set itself up while this one runs (common.cuh)
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.tm_x[0]);
@@ -164,6 +165,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) conv_pair_kernel(const __grid_c
   ptx2::cluster_sync();  // both CTAs' barriers are initialised before anything arrives on them remotely
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();  // the previous launch's results are visible from here on
 
   const int planes = p.planes;
   const int half_rows = p.n_tile >> 1;                                   // weight rows this CTA holds per tap
@@ -585,13 +587,15 @@ int conv_pair_launch(const PairLaunch* l, cudaStream_t st) {
   cfg.blockDim = dim3(PR_THREADS, 1, 1);
   cfg.dynamicSmemBytes = l->smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_mode() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, k, l->p);
   if (e != cudaSuccess) return cuda_fail(e, "conv_pair_kernel launch");
   return BVG_OK;

@@ -282,6 +282,7 @@ __global__ void __launch_bounds__(FUSED ? UM_THREADS_FUSED : 128 + 32 * UM_EPI_W
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
+  pdl_trigger();  // the next launch of the chain may set itself up while this one runs (common.cuh)
 
   if (warp == 0 && lane == 0) {
     if (!FUSED) ptx::prefetch_tmap(&p.tm_x[0]);
@@ -315,6 +316,7 @@ __global__ void __launch_bounds__(FUSED ? UM_THREADS_FUSED : 128 + 32 * UM_EPI_W
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();  // everything above overlapped the previous launch; its results are visible from here on
 
   const int planes = p.planes;
   const int stage_cols = p.mb * p.col_stride;
@@ -910,7 +912,7 @@ int conv_umma_launch(const UmmaLaunch* l, cudaStream_t st) {
   // opt in to > 48 KB of dynamic shared memory once per (device, specialisation): the attribute is per device
   if (first_use_on_device(reinterpret_cast<const void*>(k)))
     BVG_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM_LIMIT));
-  k<<<l->grid, l->p.f_x ? UM_THREADS_FUSED : 128 + 32 * l->p.epi_warps, l->smem, st>>>(l->p);
+  BVG_CHECK_CUDA(launch_k(k, dim3(l->grid), dim3(l->p.f_x ? UM_THREADS_FUSED : 128 + 32 * l->p.epi_warps), l->smem, st, l->p));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "conv_umma_kernel launch");
   return BVG_OK;

@@ -300,6 +300,8 @@ template <int OUT_MODE>
 __global__ void pack_mel_kernel(const float* __restrict__ mel, void* out, void* out_lo, int C, int T, int c_pad, const float* __restrict__ range,
                                 const float* __restrict__ mn) {
   __shared__ float tile[32][33];
+  pdl_trigger();  // programmatic dependent launch (common.cuh): no global access before the wait
+  pdl_wait();
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
@@ -339,14 +341,13 @@ int pack_mel(const bvg_pack_desc* d, cudaStream_t st) {
   BVG_REQUIRE((d->d_range == nullptr) == (d->d_min == nullptr), "pack_mel: d_range and d_min go together");
   dim3 grid(ceil_div(d->T, 32), ceil_div(d->c_pad, 32), d->B), block(32, 8);
   if (d->out.dtype == BVG_F32)
-    pack_mel_kernel<BVG_F32><<<grid, block, 0, st>>>(d->d_mel, d->out.d_ptr, nullptr, d->C, d->T, d->c_pad, d->d_range, d->d_min);
+    BVG_CHECK_CUDA(launch_k(pack_mel_kernel<BVG_F32>, grid, block, 0, st, d->d_mel, d->out.d_ptr, (void*)nullptr, d->C, d->T, d->c_pad, d->d_range, d->d_min));
   else if (d->out.dtype == BVG_BF16)
-    pack_mel_kernel<BVG_BF16><<<grid, block, 0, st>>>(d->d_mel, d->out.d_ptr, nullptr, d->C, d->T, d->c_pad, d->d_range, d->d_min);
+    BVG_CHECK_CUDA(launch_k(pack_mel_kernel<BVG_BF16>, grid, block, 0, st, d->d_mel, d->out.d_ptr, (void*)nullptr, d->C, d->T, d->c_pad, d->d_range, d->d_min));
   else if (d->out.dtype == BVG_SPLIT)
-    pack_mel_kernel<BVG_SPLIT><<<grid, block, 0, st>>>(d->d_mel, d->out.d_ptr, d->out.d_lo, d->C, d->T, d->c_pad, d->d_range, d->d_min);
+    BVG_CHECK_CUDA(launch_k(pack_mel_kernel<BVG_SPLIT>, grid, block, 0, st, d->d_mel, d->out.d_ptr, d->out.d_lo, d->C, d->T, d->c_pad, d->d_range, d->d_min));
   else
     BVG_REQUIRE(false, "pack_mel: bad dtype");
-  BVG_CHECK_CUDA(cudaGetLastError());
   return BVG_OK;
 }
 

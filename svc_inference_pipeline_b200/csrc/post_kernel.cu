@@ -12,8 +12,10 @@ template <bool IN_BF16>
 __global__ void __launch_bounds__(256) post_kernel(const void* __restrict__ x, const float* __restrict__ w, float bias,
                                                    float* __restrict__ out, int L, int C, int K, long long total) {
   extern __shared__ float ws[];
+  pdl_trigger();  // programmatic dependent launch (common.cuh); the weights were packed at load time
   for (int i = threadIdx.x; i < C * K; i += blockDim.x) ws[i] = w[i];
   __syncthreads();
+  pdl_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int t = (int)(idx % L);
@@ -63,10 +65,9 @@ int post_forward(const bvg_post_desc* d, cudaStream_t st) {
   BVG_REQUIRE(blocks < (1ll << 31), "post: grid too large");
   const size_t smem = (size_t)d->C * d->ksize * sizeof(float);
   if (d->x.dtype == BVG_BF16)
-    post_kernel<true><<<(unsigned)blocks, 256, smem, st>>>(d->x.d_ptr, d->d_w, d->bias, d->d_out, d->L, d->C, d->ksize, total);
+    BVG_CHECK_CUDA(launch_k(post_kernel<true>, dim3((unsigned)blocks), dim3(256), smem, st, d->x.d_ptr, d->d_w, d->bias, d->d_out, d->L, d->C, d->ksize, total));
   else
-    post_kernel<false><<<(unsigned)blocks, 256, smem, st>>>(d->x.d_ptr, d->d_w, d->bias, d->d_out, d->L, d->C, d->ksize, total);
-  BVG_CHECK_CUDA(cudaGetLastError());
+    BVG_CHECK_CUDA(launch_k(post_kernel<false>, dim3((unsigned)blocks), dim3(256), smem, st, d->x.d_ptr, d->d_w, d->bias, d->d_out, d->L, d->C, d->ksize, total));
   return BVG_OK;
 }
 

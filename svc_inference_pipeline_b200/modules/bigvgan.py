@@ -209,6 +209,10 @@ class _Program:
     def run(self, stream):
         L.check(L.lib().bvg_program_run(self.handle, stream), "program_run")
 
+    def set_pdl(self, on: bool):
+        """Programmatic dependent launch between the program's kernels (``bvg_program_set_pdl``)."""
+        L.check(L.lib().bvg_program_set_pdl(self.handle, int(bool(on))), "program_set_pdl")
+
     def __del__(self):
         try:
             if self.handle:
@@ -275,6 +279,9 @@ class Generator(nn.Module):
         # off for the bf16 path (since the CTA-pair convolutions: 40.1-41.2 ms on one stream, 41.3-41.8 ms on two).
         self.overlap_streams = None
         self.overlap_parts = 2
+        # Programmatic dependent launch between the kernels of a program (bvg_program_set_pdl): the set-up of launch
+        # i + 1 overlaps launch i.  See set_pdl().
+        self.pdl = False
         self._side_streams = None
         self._mel_denorm = None  # (range, min) device tensors when forward() takes mels normalised to [-1, 1]
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
@@ -601,9 +608,18 @@ class Generator(nn.Module):
         ops.append(op)
         labels.append(("conv_post+tanh", "post", 0.0))
         prog = _Program(ops, keep, mel_in, out, len(ops))
+        prog.set_pdl(self.pdl)
         prog.labels = labels
         prog.descs = descs  # ctypes descriptors the ops point to
         return prog
+
+    def set_pdl(self, on: bool):
+        """Chain the kernels of every program with programmatic dependent launch (captured graphs are re-captured)."""
+        self.pdl = bool(on)
+        for prog in self._programs.values():
+            prog.set_pdl(self.pdl)
+            prog.graph = None
+        return self
 
     def _program(self, B: int, T: int, slot: int = -1, mel_in=None, out=None) -> _Program:
         # slot >= 0: one of the half-batch programs of the overlapped forward (own workspace each; mel_in / out are

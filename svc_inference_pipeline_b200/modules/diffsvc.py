@@ -41,9 +41,12 @@ from torch import nn
 from .. import _lib as L
 from .bigvgan import _Buf, _NULL, _PackedConv, _Program
 
-__all__ = ["DiffSVC", "StepEncoder"]
+__all__ = ["DiffSVC", "StepEncoder", "DiffusionState"]
 
 _MODES = {"fp32": (L.UMMA, L.SPLIT), "bf16": (L.UMMA, L.BF16), "fp32_simt": (L.SIMT, L.F32)}
+# rows of the sampler's schedule table (the globals of reference modules/diffsvcrepo_inference.py:177-197)
+SCHEDULE_ROWS = ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1", "posterior_mean_coef2",
+                 "posterior_log_variance_clipped", "alphas_cumprod")
 
 
 class _Conv(nn.Module):
@@ -142,6 +145,8 @@ class DiffSVC(nn.Module):
         if self.channels % 8 or self.cond_size % 8:
             raise ValueError("residual_channels and conditioner_size must be multiples of 8 for the tensor-core path")
         self.use_cuda_graph = True
+        # programmatic dependent launch between the ~106 short kernels of a step (bvg_program_set_pdl)
+        self.pdl = True
         self._packed = None
         self._programs = {}
         self._cond_key = None
@@ -156,6 +161,12 @@ class DiffSVC(nn.Module):
     def _apply(self, fn, *args, **kwargs):
         self._invalidate()
         return super()._apply(fn, *args, **kwargs)
+
+    def set_pdl(self, on: bool):
+        self.pdl = bool(on)
+        self._programs = {}
+        self._cond_key = None
+        return self
 
     def set_precision(self, precision: str):
         if precision not in _MODES:
@@ -298,6 +309,24 @@ class DiffSVC(nn.Module):
         prog = _Program(ops, keep, mel_in, out, len(ops))
         prog.cond_prog = _Program(cops, keep, cond_in, None, len(cops))
         prog.cond_in, prog.step_in = cond_in, step_in
+        if not float_steps:
+            # sampler (modules/diffsvcrepo_inference.py): the step followed by the DDPM update of the sample, which
+            # lives in mel_in -- one program, one graph replay per diffusion step
+            n_steps = pk["table"].shape[0]
+            prog.tables = torch.zeros(6, n_steps, dtype=torch.float32, device=dev)   # rows: SCHEDULE_ROWS
+            prog.noise = torch.zeros(B, 1, self.n_mel, Ln, dtype=torch.float32, device=dev)
+            sop = L.Op()
+            sop.kind = L.OP_SAMPLE
+            sd = sop.u.sample
+            sd.mode, sd.clip = L.SAMPLE_DDPM, 1
+            sd.d_x, sd.d_x_out, sd.d_eps, sd.d_noise, sd.d_step = mel_in.data_ptr(), mel_in.data_ptr(), out.data_ptr(), prog.noise.data_ptr(), step_in.data_ptr()
+            row = lambda k: prog.tables.data_ptr() + 4 * k * n_steps
+            sd.d_sqrt_recip, sd.d_sqrt_recipm1, sd.d_coef1, sd.d_coef2, sd.d_logvar, sd.d_alphas_cumprod = (row(k) for k in range(6))
+            sd.B, sd.L, sd.n_mel, sd.n_steps = B, Ln, self.n_mel, n_steps
+            prog.ddpm_prog = _Program(ops + [sop], keep, mel_in, out, len(ops) + 1)
+            prog.ddpm_prog.set_pdl(self.pdl)
+        prog.set_pdl(self.pdl)
+        prog.cond_prog.set_pdl(self.pdl)
         return prog
 
     def _program(self, B, Ln, float_steps=False):
@@ -334,25 +363,117 @@ class DiffSVC(nn.Module):
             step = step.expand(B)
         prog = self._program(B, Ln, float_steps)
         with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev)
-            # same tensor OBJECT (weak reference: a freed tensor's address may be reused), unmodified since, same program
-            ck = self._cond_key
-            fresh = ck is None or ck[0]() is not conditioner or ck[1] != conditioner._version or ck[2] is not prog
-            if fresh:  # new conditioner: its 20 projections once, reused by every step that follows
-                prog.cond_in.copy_(conditioner, non_blocking=True)
-                prog.cond_prog.run(stream.cuda_stream)
-                self._cond_key = (weakref.ref(conditioner), conditioner._version, prog)
+            self._set_conditioner(prog, conditioner, dev)
             prog.mel_in.copy_(mel_spec, non_blocking=True)
             prog.step_in.copy_(step.to(prog.step_in.dtype), non_blocking=True)
-            if self.use_cuda_graph:
-                if prog.graph is None:
-                    prog.run(stream.cuda_stream)  # warm-up outside capture (lazy function attributes)
-                    stream.synchronize()
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
-                        prog.run(torch.cuda.current_stream(dev).cuda_stream)
-                    prog.graph = g
-                prog.graph.replay()
-            else:
-                prog.run(stream.cuda_stream)
+            self._launch(prog, dev)
             return prog.out.clone(), {}
+
+    def _launch(self, prog, dev):
+        """Issue a program on the current stream: a CUDA-graph replay (captured on first use) or the launch list."""
+        stream = torch.cuda.current_stream(dev)
+        if not self.use_cuda_graph:
+            prog.run(stream.cuda_stream)
+            return
+        if prog.graph is None:
+            keep = [t.clone() for t in (prog.mel_in, prog.out)]  # the warm-up and the capture must not move the sampler's state
+            prog.run(stream.cuda_stream)  # warm-up outside capture (lazy function attributes)
+            stream.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                prog.run(torch.cuda.current_stream(dev).cuda_stream)
+            prog.graph = g
+            prog.mel_in.copy_(keep[0])
+            prog.out.copy_(keep[1])
+        prog.graph.replay()
+
+    def _set_conditioner(self, prog, conditioner, dev):
+        stream = torch.cuda.current_stream(dev)
+        # same tensor OBJECT (weak reference: a freed tensor's address may be reused), unmodified since, same program
+        ck = self._cond_key
+        fresh = ck is None or ck[0]() is not conditioner or ck[1] != conditioner._version or ck[2] is not prog
+        if fresh:  # new conditioner: its 20 projections once, reused by every step that follows
+            prog.cond_in.copy_(conditioner, non_blocking=True)
+            prog.cond_prog.run(stream.cuda_stream)
+            self._cond_key = (weakref.ref(conditioner), conditioner._version, prog)
+
+    def sampler(self, conditioner: torch.Tensor, schedule_tables) -> "DiffusionState":
+        """State of one sampling run over ``conditioner [B, L, cond]`` (used by ``modules/diffsvcrepo_inference.py``)."""
+        dev = self._require_cuda()
+        B, Ln, cs = conditioner.shape
+        if cs != self.cond_size:
+            raise ValueError(f"expected conditioner of shape [B, L, {self.cond_size}], got {tuple(conditioner.shape)}")
+        prog = self._program(B, Ln, False)
+        tables = torch.as_tensor(schedule_tables, dtype=torch.float32)
+        if tables.dim() != 2 or tables.shape[0] != 6 or tables.shape[1] > prog.tables.shape[1]:
+            raise ValueError(f"schedule tables must be [6, n <= {prog.tables.shape[1]}] (the denoiser's step embedding has {prog.tables.shape[1]} rows), got {tuple(tables.shape)}")
+        with torch.cuda.device(dev):
+            self._set_conditioner(prog, conditioner, dev)
+            prog.tables.zero_()
+            prog.tables[:, : tables.shape[1]].copy_(tables)
+        return DiffusionState(self, prog, dev, tables.shape[1])
+
+
+class DiffusionState:
+    """The sample ``x [B, L, n_mel]`` of one run of the sampler and the launches that move it (reference
+    ``modules/diffsvcrepo_inference.py``).  ``x`` is the denoiser program's input buffer and ``eps`` its output buffer, so
+    a diffusion step is the program (a CUDA-graph replay) plus one ``bvg_sample_fwd`` update and nothing is copied."""
+
+    def __init__(self, model: DiffSVC, prog, dev, n_steps: int):
+        self.model, self.prog, self.dev, self.n_steps = model, prog, dev, n_steps
+        self.x, self.eps, self.noise = prog.mel_in, prog.out, prog.noise
+        self._hist = []      # PLMS: earlier predictions, most recent first (the reference's noise_list, deque(maxlen=4))
+        self._spare = [torch.empty_like(prog.out) for _ in range(4)]
+        self._x_keep = None
+
+    def _check(self, step: int):
+        if not 0 <= int(step) < self.n_steps:
+            raise IndexError(f"diffusion step {step} outside the schedule of {self.n_steps} steps")
+
+    def denoise(self, step: int):
+        """``eps = denoise_fn(x, cond, step)`` (every batch item at the same step, like the sampler's ``torch.full``)."""
+        self._check(step)
+        with torch.cuda.device(self.dev):
+            self.prog.step_in.fill_(int(step))
+            self.model._launch(self.prog, self.dev)
+
+    def ddpm_step(self, step: int):
+        """``p_sample`` (``:88-97``) with the noise in ``self.noise`` ([B, 1, n_mel, L], the reference's ``randn(x.shape)``)."""
+        self._check(step)
+        with torch.cuda.device(self.dev):
+            self.prog.step_in.fill_(int(step))
+            self.model._launch(self.prog.ddpm_prog, self.dev)
+
+    def _update(self, step, interval, combine, x_src, hist, save):
+        d = L.SampleDesc()
+        d.mode, d.clip = L.SAMPLE_PLMS, 0
+        d.d_x, d.d_x_out, d.d_eps, d.d_step = x_src.data_ptr(), self.x.data_ptr(), self.eps.data_ptr(), self.prog.step_in.data_ptr()
+        d.d_alphas_cumprod = self.prog.tables.data_ptr() + 4 * 5 * self.prog.tables.shape[1]
+        for k, h in enumerate(hist):
+            d.d_hist[k] = h.data_ptr()
+        d.d_eps_save = save.data_ptr() if save is not None else None
+        d.interval, d.combine = int(interval), int(combine)
+        d.B, d.L, d.n_mel = self.x.shape
+        d.n_steps = self.prog.tables.shape[1]
+        with torch.cuda.device(self.dev):
+            self.prog.step_in.fill_(int(step))
+            L.check(L.lib().bvg_sample_fwd(C.byref(d), torch.cuda.current_stream(self.dev).cuda_stream), "sample")
+
+    def plms_step(self, step: int, interval: int):
+        """``p_sample_plms`` (``:100-150``): pseudo linear multistep update with the last three predictions."""
+        self._check(step)
+        self.denoise(step)
+        save = self._spare.pop()
+        if not self._hist:
+            # first step: predictor with eps, second evaluation at the predicted point, average (:126-139)
+            if self._x_keep is None:
+                self._x_keep = torch.empty_like(self.x)
+            self._x_keep.copy_(self.x)
+            self._update(step, interval, 0, self.x, [], save)            # x <- get_x_pred(x, eps, t); save <- eps
+            self.denoise(max(int(step) - int(interval), 0))
+            self._update(step, interval, 1, self._x_keep, [save], None)  # x <- get_x_pred(x_keep, (save + eps) / 2, t)
+        else:
+            self._update(step, interval, min(len(self._hist), 3) + 1, self.x, self._hist[:3], save)
+        self._hist.insert(0, save)
+        if len(self._hist) > 3:
+            self._spare.append(self._hist.pop())

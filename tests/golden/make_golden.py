@@ -343,9 +343,61 @@ def golden_diffsvc():
     save("diffsvc.npz", **out)
 
 
+def golden_sampler():
+    """Diffusion sampler (the caller of the denoiser step): the UNMODIFIED reference ``modules/diffsvcrepo_inference.py::
+    svc_model_inference`` around the unmodified reference DiffSVC (a 4-layer, 64-channel mapper: the sampler is
+    independent of the denoiser's size), 12-step schedule, N = 2 and N = 1.  The reference draws its noise from the
+    global generator: the draws are reproduced here by re-seeding and repeating its calls (``torch.normal`` of
+    batch["y"].shape, then one ``torch.randn(x.shape)`` per step, last step first) and saved with the outputs (float32
+    only: a float64 run of the reference would draw different numbers).
+    ``fast``: the PLMS branch, which in the reference fails on its own denoiser's (noise, stats) tuple; it is run
+    with a denoiser wrapper that returns the tensor alone (speedup 3 -> steps 9, 6, 3, 0 = all four branches)."""
+    from modules import diffsvc as ref_d
+    from modules import diffsvcrepo_inference as ref_s
+
+    mcfg = dict(noise_schedule_factors=[0.0001, 0.02, 1000], n_mel=100, residual_channels=64, diffusion_fc_size=128, conditioner_size=64,
+                dilation_cycle_length=4, residual_kernel_size=3, residual_layer_num=4)
+    model = ref_d.DiffSVC(JsonHParams(**mcfg)).eval()
+    sd = synth.synthetic_diffsvc_state_dict(mcfg, seed=5)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    sched = np.linspace(1e-4, 0.35, 12).tolist()
+    cfg = JsonHParams(mapper=JsonHParams(noise_schedule=sched))
+    out = dict(noise_schedule=np.asarray(sched))
+
+    class Cond(torch.nn.Module):
+        def forward(self, batch):
+            return batch["cond"]
+
+    class TensorOnly(torch.nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+
+        def forward(self, *a):
+            return self.m(*a)[0]
+
+    for tag, (N, T) in {"n2": (2, 61), "n1": (1, 96)}.items():
+        cond = torch.from_numpy(rnd((N, T, mcfg["conditioner_size"]), 70 + N))
+        batch = {"y": torch.zeros(N, T, mcfg["n_mel"]), "cond": cond}
+        seed = 900 + N
+        torch.manual_seed(seed)
+        x0 = torch.normal(0, 1 / 1.2, size=batch["y"].shape)
+        steps = torch.zeros(len(sched), N, 1, mcfg["n_mel"], T)
+        for i in reversed(range(len(sched))):
+            steps[i] = torch.randn(N, 1, mcfg["n_mel"], T)
+        torch.manual_seed(seed)
+        y = ref_s.svc_model_inference(torch.nn.ModuleList([Cond(), model]), batch, cfg)
+        out[tag + "_y"] = y.numpy()
+        torch.manual_seed(seed)
+        yf = ref_s.svc_model_inference(torch.nn.ModuleList([Cond(), TensorOnly(model)]), batch, cfg, fast_inference=True, speedup=3)
+        out.update({tag + "_cond": cond.numpy(), tag + "_x0": x0.numpy(), tag + "_noise": steps.numpy(), tag + "_fast": yf.numpy()})
+        print(f"sampler {tag}: out {tuple(y.shape)}, clamped at the last step {float((y.abs() >= 1).float().mean()):.2f}, fast |y|max {float(yf.abs().max()):.3f}")
+    save("sampler.npz", **out)
+
+
 STEPS = {
     "mel_range": mel_range_fixture, "filters": golden_filters, "activation": golden_activation, "convs": golden_convs, "tiny": golden_tiny,
-    "repo": golden_repo, "bench_item": golden_bench_item, "v2_long": golden_v2_long, "recipes": golden_recipes, "logmel": golden_logmel, "diffsvc": golden_diffsvc,
+    "repo": golden_repo, "bench_item": golden_bench_item, "v2_long": golden_v2_long, "recipes": golden_recipes, "logmel": golden_logmel, "diffsvc": golden_diffsvc, "sampler": golden_sampler,
 }
 
 if __name__ == "__main__":

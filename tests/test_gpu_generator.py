@@ -168,6 +168,35 @@ def test_cuda_graph_matches_eager(golden):
     assert torch.equal(y0, y1) and torch.equal(y2, y3)
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_programmatic_dependent_launch_is_identical(repo_model, precision):
+    """Generator.set_pdl: the same launches chained with programmatic dependent launch (every kernel waits for its
+    predecessor's results before its first global access) give bit-identical waveforms -- one program, two overlapped
+    half-batch programs, CUDA graph -- and stay identical over repeated calls (no read of a buffer the previous
+    launch is still writing)."""
+    from svc_inference_pipeline_b200.utils import synth
+
+    mel = torch.from_numpy(synth.synthetic_mel(3, 100, 61, seed=37)).to(DEV)
+    try:
+        repo_model.set_precision(precision)
+        ref = repo_model(mel)
+        ref1 = repo_model(mel[:1])
+        repo_model.set_pdl(True)
+        for _ in range(3):
+            assert torch.equal(repo_model(mel), ref)
+        repo_model.overlap_streams = False
+        for _ in range(3):
+            assert torch.equal(repo_model(mel), ref)
+        repo_model.use_cuda_graph = True
+        for _ in range(3):
+            assert torch.equal(repo_model(mel[:1]), ref1)
+    finally:
+        repo_model.use_cuda_graph = False
+        repo_model.overlap_streams = None
+        repo_model.set_pdl(False)
+        repo_model.set_precision("fp32")
+
+
 def test_vocode_long_matches_full(repo_model):
     """Long-form path: time chunks with a 48-frame halo + 20-frame cross-fade reproduce the
     unchunked forward (the receptive field is +-38 frames)."""

@@ -16,6 +16,8 @@ ap.add_argument("--v2", action="store_true", help="BASELINE configs[4]: 512x gen
                                                   "one rank's share of B64 x 30 s on 8 GPUs is --batch 8 --frames 2584")
 ap.add_argument("--tune", action="append", default=[], help="name=value tuning knob (bvg_tuning, attached to every descriptor built afterwards)")
 ap.add_argument("--parts", default="0,2", help="overlap settings to time (0 = one stream, n = n batch parts on n streams)")
+ap.add_argument("--pdl", type=int, default=0, help="programmatic dependent launch between the kernels (Generator.set_pdl)")
+ap.add_argument("--graph", type=int, default=0, help="replay the forward as a CUDA graph")
 a = ap.parse_args()
 from svc_inference_pipeline_b200 import _lib as _L
 for kv in a.tune:
@@ -31,6 +33,8 @@ from svc_inference_pipeline_b200.utils.util import JsonHParams
 m = Generator(JsonHParams(**vc))
 m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.synthetic_state_dict(vc, 0).items()})
 m = m.cuda().eval()
+m.set_pdl(bool(a.pdl))
+m.use_cuda_graph = bool(a.graph)
 mel = torch.from_numpy(synth.synthetic_mel(a.batch, vc["input_dim"], a.frames, 1235)).cuda()
 for prec in a.precisions.split(","):
     m.set_precision(prec)
@@ -49,6 +53,6 @@ for prec in a.precisions.split(","):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / a.reps
         outs[ov] = y
-        print(f"{prec} overlap={ov}: {ms:.2f} ms/step, {a.batch * a.frames * hop / fs / (ms / 1e3):.0f} audio-s/s", flush=True)
+        print(f"{prec} pdl={a.pdl} graph={a.graph} overlap={ov}: {ms:.3f} ms/step, {a.batch * a.frames * hop / fs / (ms / 1e3):.0f} audio-s/s", flush=True)
     if len(outs) > 1:
         print(f"{prec} max |overlap - plain| = {max(float((outs[k] - outs[0]).abs().max()) for k in outs if k):.3e}")
