@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BVG_ABI_VERSION 5  /* 2: bvg_conv_geom.fold, bvg_conv_desc.pre_amp; 3: bvg_stitch_fwd; 4: bvg_tuning in the descriptors (bvg_set_tuning removed), bvg_logmel_fwd, bvg_rowop_fwd, bvg_diffembed_fwd, bvg_conv_desc.relu; 5: bvg_sample_fwd, bvg_program_set_pdl */
+#define BVG_ABI_VERSION 5  /* 2: bvg_conv_geom.fold, bvg_conv_desc.pre_amp; 3: bvg_stitch_fwd; 4: bvg_tuning in the descriptors (bvg_set_tuning removed), bvg_logmel_fwd, bvg_rowop_fwd, bvg_diffembed_fwd, bvg_conv_desc.relu; 5: bvg_sample_fwd, bvg_program_set_pdl, bvg_conv_desc.d_coldiv */
 
 enum bvg_status {
   BVG_OK = 0,
@@ -161,6 +161,10 @@ typedef struct bvg_conv_desc {
   int32_t relu;        /* 1: out = max(out, 0) as the last epilogue step (the F.relu after the 1x1 projections of the
                           DiffSVC denoiser, modules/diffsvc.py:126, :316) */
   int32_t _pad;
+  const float* d_coldiv; /* optional [n_total]: out[.., n] /= d_coldiv[n] (a true division per output channel) instead of
+                            the scalar div, which must then be 1.  One launch for the DiffSVC residual layer's
+                            output_projection (modules/diffsvc.py:229-232, :307): channels [0, C) are "(x + residual) /
+                            sqrt(2)", channels [C, 2C) the skip sum (divisor 1), with res = out = the [x | skip] buffer. */
 } bvg_conv_desc;
 
 int bvg_conv_fwd(const bvg_conv_desc* d, void* stream);

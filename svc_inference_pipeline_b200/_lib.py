@@ -87,6 +87,7 @@ class ConvDesc(C.Structure):
         ("tune", C.POINTER(Tuning)),
         ("relu", C.c_int32),
         ("_pad", C.c_int32),
+        ("d_coldiv", C.c_void_p),  # const float* [n_total]: per-channel divisor (or NULL)
     ]
 
 
@@ -349,6 +350,19 @@ def set_tuning(name: str, value: int) -> None:
 def reset_tuning() -> None:
     t, _ = _tuning_state()
     lib().bvg_tuning_defaults(C.byref(t))
+
+
+def new_tuning(**knobs):
+    """A ``Tuning`` of the caller's own: the binding's current knobs with ``knobs`` on top (pass ``ctypes.pointer`` of it as
+    a descriptor's ``tune``; geometry and programs read it at creation and keep their own copy)."""
+    t, _ = _tuning_state()
+    own = Tuning()
+    C.memmove(C.byref(own), C.byref(t), C.sizeof(Tuning))
+    for name, value in knobs.items():
+        if name not in dict(Tuning._fields_) or name.startswith("_"):
+            raise BvgError(f"unknown tuning knob '{name}'")
+        setattr(own, name, int(value))
+    return own
 
 
 def tuning_ptr():

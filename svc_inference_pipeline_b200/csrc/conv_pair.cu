@@ -391,6 +391,11 @@ __global__ void __launch_bounds__(PR_THREADS, 1) conv_pair_kernel(const __grid_c
 #pragma unroll
               for (int j = 0; j < 4; ++j) v[i][j] = __fdiv_rn(v[i][j], p.epi.div);
             }
+            if (p.epi.coldiv) {
+              const float4 cd = *reinterpret_cast<const float4*>(p.epi.coldiv + n0);
+              v[i][0] = __fdiv_rn(v[i][0], cd.x); v[i][1] = __fdiv_rn(v[i][1], cd.y);
+              v[i][2] = __fdiv_rn(v[i][2], cd.z); v[i][3] = __fdiv_rn(v[i][3], cd.w);
+            }
             if (p.epi.relu) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) v[i][j] = fmaxf(v[i][j], 0.f);

@@ -588,6 +588,11 @@ __global__ void __launch_bounds__(FUSED ? UM_THREADS_FUSED : 128 + 32 * UM_EPI_W
 #pragma unroll
                 for (int j = 0; j < 4; ++j) v[i][j] = __fdiv_rn(v[i][j], p.epi.div);
               }
+              if (GEN && p.epi.coldiv) {
+                const float4 cd = *reinterpret_cast<const float4*>(p.epi.coldiv + n0);
+                v[i][0] = __fdiv_rn(v[i][0], cd.x); v[i][1] = __fdiv_rn(v[i][1], cd.y);
+                v[i][2] = __fdiv_rn(v[i][2], cd.z); v[i][3] = __fdiv_rn(v[i][3], cd.w);
+              }
               if (GEN && p.epi.relu) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) v[i][j] = fmaxf(v[i][j], 0.f);
@@ -881,7 +886,7 @@ static UmmaKernel select_kernel(const UmmaParams& p) {
   const bool res = e.res != nullptr, acc = e.acc != nullptr;
   const bool sbf = (res && e.res_dtype == BVG_BF16) || (acc && e.acc_dtype == BVG_BF16);
   const bool mixed = (res && acc && e.res_dtype != e.acc_dtype);
-  const bool plain = p.vec_ok && !mixed && (acc || !e.use_div) && (!acc || res) && !e.relu;
+  const bool plain = p.vec_ok && !mixed && (acc || !e.use_div) && (!acc || res) && !e.relu && !e.coldiv;
   if (p.f_x) {  // fused Activation1d producer: the epilogues the fp32 path's resblock convolutions use, else the generic one
     if (plain && !sbf) {
       if (e.out_dtype == BVG_F32 && !res) return conv_umma_kernel<BVG_F32, false, false, false, false, true>;

@@ -14,6 +14,7 @@ struct EpiParams {
   const void* res;
   const void* acc;
   const float* bias;
+  const float* coldiv;  // per-column divisor (then use_div = 0)
   float div;
   int out_dtype, res_dtype, acc_dtype;
   int use_div;
@@ -80,6 +81,10 @@ __device__ __forceinline__ void epilogue4(const EpiParams& e, long long row, int
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = __fdiv_rn(v[i], e.div);
   }
+  if (e.coldiv) {
+    const float4 cd = *reinterpret_cast<const float4*>(e.coldiv + n0);
+    v[0] = __fdiv_rn(v[0], cd.x); v[1] = __fdiv_rn(v[1], cd.y); v[2] = __fdiv_rn(v[2], cd.z); v[3] = __fdiv_rn(v[3], cd.w);
+  }
   if (e.relu) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -104,6 +109,7 @@ __device__ __forceinline__ void epilogue1(const EpiParams& e, long long row, int
   if (e.res) v += epi_load1(e.res, e.res_dtype, off);
   if (e.acc) v += epi_load1(e.acc, e.acc_dtype, off);
   if (e.use_div) v = __fdiv_rn(v, e.div);
+  if (e.coldiv) v = __fdiv_rn(v, e.coldiv[n]);
   if (e.relu) v = fmaxf(v, 0.f);
   if (e.out_dtype == BVG_F32) {
     reinterpret_cast<float*>(e.out)[off] = v;
@@ -127,7 +133,10 @@ inline int fill_epilogue(const bvg_conv_desc* d, EpiParams& e) {
   e.acc_dtype = d->acc_in.dtype;
   e.bias = d->w->d_bias;
   e.div = d->div;
+  e.coldiv = d->d_coldiv;
   e.use_div = (d->div != 1.0f && d->div != 0.0f) ? 1 : 0;
+  BVG_REQUIRE(!(e.coldiv && e.use_div), "conv: d_coldiv and div != 1 exclude each other");
+  BVG_REQUIRE(!e.coldiv || (((uintptr_t)e.coldiv) & 15) == 0, "conv: d_coldiv must be 16-byte aligned");
   e.relu = d->relu ? 1 : 0;
   e.N = d->w->n_total;
   BVG_REQUIRE(e.out != nullptr, "conv: null output");

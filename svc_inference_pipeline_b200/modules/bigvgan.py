@@ -160,14 +160,14 @@ _NULL = L.Tensor(None, None, L.F32, 0)
 class _PackedConv:
     """Folded + packed weights of one conv layer, resident on the device."""
 
-    def __init__(self, conv: _WNConv, backend: int, split: bool, stream, fold: int = 1):
+    def __init__(self, conv: _WNConv, backend: int, split: bool, stream, fold: int = 1, tune=None):
         lib = L.lib()
         dev = conv.weight_v.device
         self.fold = int(fold) if fold and fold > 1 else 1  # time folding (include/bvg_b200.h, bvg_conv_geom.fold)
         self.geom = L.ConvGeom(
             int(conv.transposed), conv.cin, conv.cout, conv.ksize, conv.dilation, conv.stride, conv.padding, backend, int(split), 0, self.fold
         )
-        tune = L.tuning_ptr()
+        tune = tune if tune is not None else L.tuning_ptr()  # a caller's own Tuning (L.new_tuning) or the binding's
         if tune is not None:
             self.geom.tune = tune
         wb, bb = C.c_size_t(), C.c_size_t()

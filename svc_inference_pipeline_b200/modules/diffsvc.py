@@ -19,8 +19,8 @@ as a CUDA graph: the step index lives in a device buffer the graph reads.  Per r
     rowop ADDVEC   y = x + diffusion_projection(step)           -> (hi, lo) operand planes          (:213)
     conv  k=3, d   dilated_conv(y) + [conditioner_projection(e)] C -> 2C on tcgen05, fp32 out       (:220)
     rowop GATE     sigmoid(gate) * tanh(filter)                  -> operand planes                   (:225-227)
-    conv  1x1      output_projection, residual half: x = (x + r) / sqrt(2)   (epilogue)             (:229-232)
-    conv  1x1      output_projection, skip half:     skip += s               (epilogue)             (:307)
+    conv  1x1      output_projection C -> 2C, in place on the [x | skip] buffer:                    (:229-232, :307)
+                   x = (x + r) / sqrt(2) | skip = s + skip   (epilogue, per-channel divisor)
 
 The conditioner does not change between the steps of one utterance, so its 20 projections ``[B, L, cond] -> [B, L, 2C]``
 (``:216-219``; the reference recomputes them every step) run once per conditioner tensor and enter the dilated
@@ -67,11 +67,14 @@ class _Conv(nn.Module):
 class _View:
     """What ``_PackedConv`` reads from a layer (``weight_v`` / ``weight_g`` / ``bias`` + geometry): a slice of a ``_Conv``."""
 
-    def __init__(self, conv: _Conv, rows=None, bias=True):
+    def __init__(self, conv: _Conv, rows=None, bias=True, zero_rows=0):
         w = conv.weight.detach()
         b = conv.bias.detach()
         if rows is not None:
             w, b = w[rows], b[rows]
+        if zero_rows:  # extra output channels that are identically zero (the skip half of the [x | skip] buffer)
+            w = torch.cat([w, w.new_zeros(zero_rows, *w.shape[1:])])
+            b = torch.cat([b, b.new_zeros(zero_rows)])
         self.weight_v, self.weight_g = w.contiguous(), None
         self.bias = b.contiguous() if bias else torch.zeros_like(b)
         self.cin, self.cout, self.ksize = conv.cin, w.shape[0], conv.ksize
@@ -147,14 +150,14 @@ class DiffSVC(nn.Module):
         self.use_cuda_graph = True
         # programmatic dependent launch between the ~106 short kernels of a step (bvg_program_set_pdl)
         self.pdl = True
-        self._packed = None
+        self._packed = {}   # tile cap -> packed weights
         self._programs = {}
         self._cond_key = None
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
 
     # -- plumbing ---------------------------------------------------------------------------------
     def _invalidate(self):
-        self._packed = None
+        self._packed = {}
         self._programs = {}
         self._cond_key = None
 
@@ -186,25 +189,36 @@ class DiffSVC(nn.Module):
         L.require_sm100(dev.index if dev.index is not None else torch.cuda.current_device())
         return dev
 
-    def _pack(self):
+    @staticmethod
+    def tile_cap(rows: int) -> int:
+        """Widest N tile of the dense layers for ``rows = B * L`` activation rows.  A step is ~86 dependent launches of a few
+        microseconds; with one utterance (379 rows = 3 row blocks) 128-column tiles occupy 12-24 of the 148 SMs and every
+        launch is one long serial chain of MMAs.  Narrow tiles spread a launch over more SMs; wide tiles re-read the
+        activations less often once the rows alone fill the GPU.  Measured (tools/profile_diffsvc.py, ms per step, fp32 /
+        bf16 path): 379 rows 0.54 / 0.47 at 32 columns, 0.68 / 0.49 at 64, 0.76 / 0.62 at 128; 1516 rows 0.79 / 0.70, 0.77 /
+        0.57, 0.83 / 0.70; 15 008 rows 4.6 / 3.1, 4.2 / 2.7, 3.1 / 2.6."""
+        return 32 if rows <= 512 else 64 if rows <= 4096 else 128
+
+    def _pack(self, cap: int):
         dev = self._require_cuda()
         backend, op_dt = _MODES[self.precision]
         split = op_dt == L.SPLIT
         stream = torch.cuda.current_stream(dev).cuda_stream
         Cc = self.channels
-        pk = {}
+        pk = {"tune": L.new_tuning(umma_ntile_cap=cap)}
+        tune = C.pointer(pk["tune"])
 
         def pack(name, view):
-            pk[name] = _PackedConv(view, backend, split, stream)
+            pk[name] = _PackedConv(view, backend, split, stream, tune=tune)
 
         with torch.cuda.device(dev):
-            pack("pre", _View(self.mel_preprocess.projection))
+            # x and the running skip sum share one [rows, 2C] buffer (see _build): the preprocessor writes [relu(.) | 0]
+            pack("pre", _View(self.mel_preprocess.projection, zero_rows=Cc))
             for i, rl in enumerate(self.residual_layers):
                 # the conditioner projection's bias rides along with the cached projection; the dilated conv keeps its own
                 pack(f"dil{i}", _View(rl.dilated_conv))
                 pack(f"cond{i}", _View(rl.conditioner_projection))
-                pack(f"res{i}", _View(rl.output_projection, rows=slice(0, Cc)))        # chunk 0: residual (:230)
-                pack(f"skip{i}", _View(rl.output_projection, rows=slice(Cc, 2 * Cc)))   # chunk 1: skip
+                pack(f"outp{i}", _View(rl.output_projection))  # both chunks (:230): [residual | skip]
             pack("skipproj", _View(self.skip_projection))
             pack("out", _View(self.output_projection))
             f32 = lambda t: t.detach().float().contiguous()
@@ -213,18 +227,21 @@ class DiffSVC(nn.Module):
             pk["wd"] = torch.stack([f32(rl.diffusion_projection.weight) for rl in self.residual_layers]).contiguous()
             pk["bd"] = torch.stack([f32(rl.diffusion_projection.bias) for rl in self.residual_layers]).contiguous()
             pk["table"] = f32(self.diffusion_embedding.embedding)
+            # per-channel divisor of the output projection's epilogue: (x + residual) / sqrt(2) | skip sum (:232, :307)
+            pk["coldiv"] = torch.cat([torch.full((Cc,), sqrt(2.0)), torch.ones(Cc)]).to(device=dev, dtype=torch.float32)
             torch.cuda.current_stream(dev).synchronize()
-        self._packed = pk
+        self._packed[cap] = pk
 
     # -- programs -----------------------------------------------------------------------------------
     def _build(self, B: int, Ln: int, float_steps: bool = False):
-        if self._packed is None:
-            self._pack()
+        rows = B * Ln
+        cap = self.tile_cap(rows)
+        if cap not in self._packed:
+            self._pack(cap)
         dev = self._device()
         backend, op_dt = _MODES[self.precision]
-        pk, Cc, nl = self._packed, self.channels, len(self.residual_layers)
-        tune = L.tuning_ptr()
-        rows = B * Ln
+        pk, Cc, nl = self._packed[cap], self.channels, len(self.residual_layers)
+        tune = C.pointer(pk["tune"])
         mel_pitch = pk["pre"].x_pitch
         keep = []
 
@@ -244,7 +261,7 @@ class DiffSVC(nn.Module):
         cond_op = _Buf(op_dt, rows * self.cond_size, dev)
         y_op = _Buf(op_dt, rows * Cc, dev)
         z_op = _Buf(op_dt, rows * Cc, dev)
-        xa, xb, skip, y2 = f32buf(rows * Cc), f32buf(rows * Cc), f32buf(rows * Cc), f32buf(rows * 2 * Cc)
+        xs, y2 = f32buf(rows * 2 * Cc), f32buf(rows * 2 * Cc)   # xs = [x | skip] per row
         condproj = [f32buf(rows * 2 * Cc) for _ in range(nl)]
         dproj = f32buf(nl * B * Cc)
         keep += [mel_in, cond_in, step_in, out, mel_op, cond_op, y_op, z_op]
@@ -257,7 +274,7 @@ class DiffSVC(nn.Module):
             d.B, d.L, d.C, d.x_pitch, d.out_pitch = B, Ln, C_, x_pitch, out_pitch
             ops.append(op)
 
-        def conv(ops, name, x, out_t, res=None, acc=None, div=1.0, relu=False):
+        def conv(ops, name, x, out_t, res=None, acc=None, div=1.0, relu=False, coldiv=None):
             op = L.Op()
             op.kind = L.OP_CONV
             d = op.u.conv
@@ -267,8 +284,8 @@ class DiffSVC(nn.Module):
             d.div, d.B, d.L = float(div), B, Ln
             d.w = C.pointer(pk[name].desc)
             d.relu = int(relu)
-            if tune is not None:
-                d.tune = tune
+            d.d_coldiv = coldiv.data_ptr() if coldiv is not None else None
+            d.tune = tune
             ops.append(op)
 
         def operand(buf):  # the SIMT anchor reads fp32 operands
@@ -294,16 +311,14 @@ class DiffSVC(nn.Module):
         d.B, d.emb, d.fc, d.C, d.n_layers, d.max_steps = B, pk["table"].shape[1], self.fc, Cc, nl, pk["table"].shape[0]
         ops.append(op)
         rowop(ops, L.ROW_ADDVEC, mel_in.data_ptr(), mel_op.tensor(), self.n_mel, self.n_mel, mel_pitch)
-        conv(ops, "pre", operand(mel_op), f32t(xa), relu=True)                                     # mel_preprocess (:118-128)
-        x_cur, x_nxt = xa, xb
+        conv(ops, "pre", operand(mel_op), f32t(xs), relu=True)                                     # mel_preprocess (:118-128) -> [x | 0]
         for i in range(nl):
-            rowop(ops, L.ROW_ADDVEC, x_cur.data_ptr(), y_op.tensor(), Cc, Cc, Cc, vec=dproj.data_ptr() + 4 * i * B * Cc)
+            rowop(ops, L.ROW_ADDVEC, xs.data_ptr(), y_op.tensor(), Cc, 2 * Cc, Cc, vec=dproj.data_ptr() + 4 * i * B * Cc)
             conv(ops, f"dil{i}", operand(y_op), f32t(y2), acc=f32t(condproj[i]))                    # dilated_conv(y) + conditioner (:220)
             rowop(ops, L.ROW_GATE, y2.data_ptr(), z_op.tensor(), Cc, 2 * Cc, Cc)
-            conv(ops, f"res{i}", operand(z_op), f32t(x_nxt), res=f32t(x_cur), div=sqrt(2.0))       # (x + residual) / sqrt(2) (:232)
-            conv(ops, f"skip{i}", operand(z_op), f32t(skip), acc=f32t(skip) if i else None)        # skip accumulation (:307)
-            x_cur, x_nxt = x_nxt, x_cur
-        rowop(ops, L.ROW_SCALE, skip.data_ptr(), y_op.tensor(), Cc, Cc, Cc, div=sqrt(nl))          # skip / sqrt(n) (:313)
+            # output_projection, both chunks in one launch, in place: x = (x + residual) / sqrt(2) | skip = s + skip (:229-232, :307)
+            conv(ops, f"outp{i}", operand(z_op), f32t(xs), res=f32t(xs), coldiv=pk["coldiv"])
+        rowop(ops, L.ROW_SCALE, xs.data_ptr() + 4 * Cc, y_op.tensor(), Cc, 2 * Cc, Cc, div=sqrt(nl))  # skip / sqrt(n) (:313)
         conv(ops, "skipproj", operand(y_op), z_op.tensor(), relu=True)                             # skip_projection + relu (:315-316)
         conv(ops, "out", operand(z_op), f32t(out))                                                  # output_projection (:317)
         prog = _Program(ops, keep, mel_in, out, len(ops))

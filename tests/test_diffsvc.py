@@ -115,7 +115,7 @@ def test_denoiser_graph_steps_and_conditioner_cache(golden):
     ref5 = DO.denoiser_forward(sd, MAPPER, mel.cpu().double(), cond2.cpu().double(), tf.double()).numpy()
     assert np.abs(y5.cpu().numpy() - ref5).max() < 1e-4
     assert float((y5 - y4).abs().max()) > 1e-3
-    assert m.launches_per_step(2, 61) == 2 + 1 + 20 * 5 + 3
+    assert m.launches_per_step(2, 61) == 2 + 1 + 20 * 4 + 3
 
 
 def test_denoiser_loader_reads_the_mapper_checkpoint(tmp_path):

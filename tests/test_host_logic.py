@@ -322,3 +322,22 @@ def test_product_mel_filterbank_is_the_pinned_one(golden):
     np.testing.assert_array_equal(mel_filterbank(24000, 1024, 100, 0, 12000), golden("logmel.npz")["basis"])
     fb = mel_filterbank(44100, 2048, 128, 0, 22050)
     assert fb.shape == (128, 1025) and (fb >= 0).all() and (fb.sum(axis=1) > 0).all()
+
+
+def test_new_tuning_is_a_private_copy():
+    """L.new_tuning: the binding's knobs with overrides on top, independent of later set_tuning calls (DiffSVC packs its
+    dense layers with a row-count dependent tile cap without touching the process-wide object)."""
+    from svc_inference_pipeline_b200 import _lib as L
+    from svc_inference_pipeline_b200.modules.diffsvc import DiffSVC
+
+    try:
+        L.reset_tuning()
+        own = L.new_tuning(umma_ntile_cap=32)
+        assert own.umma_ntile_cap == 32 and own.umma_pair == 1 and L.tuning_ptr() is None
+        L.set_tuning("umma_pair", 0)
+        assert own.umma_pair == 1 and L.new_tuning().umma_pair == 0
+        with pytest.raises(L.BvgError):
+            L.new_tuning(no_such_knob=1)
+    finally:
+        L.reset_tuning()
+    assert [DiffSVC.tile_cap(r) for r in (379, 512, 513, 4096, 4097, 15008)] == [32, 32, 64, 64, 128, 128]

@@ -14,7 +14,12 @@ ap.add_argument("--batch", type=int, default=1)
 ap.add_argument("--frames", type=int, default=379)
 ap.add_argument("--precision", default="fp32")
 ap.add_argument("--eager", type=int, default=1)
+ap.add_argument("--tune", action="append", default=[], help="name=value tuning knob (bvg_tuning)")
+ap.add_argument("--brief", type=int, default=0)
 a = ap.parse_args()
+for kv in a.tune:
+    k, v = kv.split("=")
+    L.set_tuning(k, int(v))
 dev = "cuda:0"
 mcfg = dict(noise_schedule_factors=[0.0001, 0.02, 1000], n_mel=100, residual_channels=384, diffusion_fc_size=128, conditioner_size=384,
             dilation_cycle_length=4, residual_kernel_size=3, residual_layer_num=20)
@@ -34,7 +39,7 @@ for _ in range(50):
     dm(mel, cond, t)
 e1.record()
 torch.cuda.synchronize()
-print(f"{a.precision} B{B}x{Ln}: forward (graph replay + copies) {e0.elapsed_time(e1) / 50:.3f} ms/step, {dm.launches_per_step(B, Ln)} launches")
+print(f"{a.precision} tune={a.tune} B{B}x{Ln}: forward (graph replay + copies) {e0.elapsed_time(e1) / 50:.3f} ms/step, {dm.launches_per_step(B, Ln)} launches")
 prog = dm._program(B, Ln)
 n = prog.launches
 per = (C.c_float * n)()
@@ -46,9 +51,11 @@ for _ in range(5):
     L.check(L.lib().bvg_program_run_timed(prog.handle, stream, ms, cnt, per), "timed")
     for i in range(n):
         acc[i] += per[i] / 5
-names = ["diffembed", "rowop mel", "conv pre"] + sum([[f"L{i} addvec", f"L{i} dilated", f"L{i} gate", f"L{i} res", f"L{i} skip"] for i in range(20)], []) + ["scale", "skipproj", "out"]
-for i in list(range(3)) + list(range(3, 3 + 20)) + list(range(n - 3, n)):
-    print(f"  {names[i]:14s} {acc[i] * 1e3:7.1f} us")
+names = ["diffembed", "rowop mel", "conv pre"] + sum([[f"L{i} addvec", f"L{i} dilated", f"L{i} gate", f"L{i} outproj"] for i in range(20)], []) + ["scale", "skipproj", "out"]
+assert len(names) == n
+if not a.brief:
+    for i in list(range(3)) + list(range(3, 3 + 16)) + list(range(n - 3, n)):
+        print(f"  {names[i]:14s} {acc[i] * 1e3:7.1f} us")
 kinds = {}
 for nm, v in zip(names, acc):
     k = nm.split()[-1] if nm.startswith("L") else nm
