@@ -456,6 +456,26 @@ def main():
                 a1.record()
                 torch.cuda.synchronize(dev)
                 dstep[f"{prec}_b{b_}x{l_}_ms"] = a0.elapsed_time(a1) / 20
+        if not args.no_eager:
+            # same-box baseline: the functional port of the reference's DiffSVC.forward (oracle/diffsvc_oracle.py, measurement
+            # only) run by PyTorch eager on this GPU, fp32 with TF32 off
+            from oracle import diffsvc_oracle as DO
+
+            sdg = {k: torch.from_numpy(v).to(dev) for k, v in synth.synthetic_diffsvc_state_dict(mcfg, seed=3).items()}
+            for (b_, l_) in ((1, 379), (16, 938)):
+                xm, xc = torch.randn(b_, l_, 100, device=dev), torch.randn(b_, l_, 384, device=dev)
+                tt = torch.full((b_, 1), 500, dtype=torch.long, device=dev)
+                for _ in range(3):
+                    DO.denoiser_forward(sdg, mcfg, xm, xc, tt)
+                torch.cuda.synchronize(dev)
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(10):
+                    DO.denoiser_forward(sdg, mcfg, xm, xc, tt)
+                a1.record()
+                torch.cuda.synchronize(dev)
+                dstep[f"torch_eager_gpu_fp32_b{b_}x{l_}_ms"] = a0.elapsed_time(a1) / 10
+            del sdg
         # the sampler that drives it (modules/diffsvcrepo_inference.py::svc_model_inference, the call infer.py:79 makes): the
         # reference's 1000-step schedule on one utterance of config 1's length, host wall clock, result copied to the host
         from svc_inference_pipeline_b200.modules.diffsvcrepo_inference import svc_model_inference
