@@ -341,3 +341,32 @@ def test_new_tuning_is_a_private_copy():
     finally:
         L.reset_tuning()
     assert [DiffSVC.tile_cap(r) for r in (379, 512, 513, 4096, 4097, 15008)] == [32, 32, 64, 64, 128, 128]
+
+
+def test_descriptor_validation_without_a_gpu():
+    """The C ABI rejects malformed descriptors before any CUDA call (runs on a box without a GPU): sampler update, row
+    operations, per-channel divisor of the convolution epilogue, program flags."""
+    from svc_inference_pipeline_b200 import _lib as L
+
+    lib = L.lib()
+    d = L.SampleDesc()
+    assert lib.bvg_sample_fwd(C.byref(d), None) == -1 and b"null pointer" in lib.bvg_last_error()
+    buf = (C.c_float * 64)()
+    p = C.addressof(buf)
+    d.d_x = d.d_x_out = d.d_eps = d.d_step = p
+    d.B, d.L, d.n_mel, d.n_steps = 1, 4, 4, 8
+    d.mode = L.SAMPLE_DDPM
+    assert lib.bvg_sample_fwd(C.byref(d), None) == -1 and b"schedule tables" in lib.bvg_last_error()
+    d.mode = L.SAMPLE_PLMS
+    assert lib.bvg_sample_fwd(C.byref(d), None) == -1 and b"alphas_cumprod" in lib.bvg_last_error()
+    d.d_alphas_cumprod, d.interval, d.combine = p, 10, 5
+    assert lib.bvg_sample_fwd(C.byref(d), None) == -1 and b"unknown combination" in lib.bvg_last_error()
+    d.combine = 3  # two earlier predictions needed, none given
+    assert lib.bvg_sample_fwd(C.byref(d), None) == -1 and b"earlier predictions" in lib.bvg_last_error()
+    d.mode = 7
+    assert lib.bvg_sample_fwd(C.byref(d), None) == -1 and b"unknown mode" in lib.bvg_last_error()
+    r = L.RowopDesc()
+    r.kind, r.d_x, r.B, r.L, r.C, r.x_pitch, r.out_pitch = L.ROW_GATE, p, 1, 4, 8, 8, 8   # GATE reads 2C channels
+    r.out = L.Tensor(p, None, L.F32, 0)
+    assert lib.bvg_rowop_fwd(C.byref(r), None) == -1 and b"row pitch" in lib.bvg_last_error()
+    assert lib.bvg_program_set_pdl(None, 1) == -1
