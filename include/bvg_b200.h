@@ -74,7 +74,8 @@ typedef struct bvg_tuning {
                               2: single-tile SPLIT layers (C = 192) on the single-CTA kernel; 4: wide SPLIT layers keep 256 / 192-column tiles */
   int32_t umma_pair_smem_kb; /* 0 = default; cap (KB) on the pair kernel's dynamic shared memory: fewer weight stages leave
                               room for Activation1d CTAs of another stream on the same SM */
-  int32_t _reserved[3];
+  int32_t umma_pair_min;     /* 0 = default (128): narrowest N tile that runs on the CTA-pair kernel (a multiple of 32) */
+  int32_t _reserved[2];
 } bvg_tuning;
 
 void bvg_tuning_defaults(bvg_tuning* t);

@@ -31,7 +31,7 @@ class Tuning(C.Structure):
 
     _fields_ = [(n, C.c_int32) for n in (
         "amp_vec", "amp_chunk", "amp_mma", "amp_mma_tiles", "amp_packed", "amp_stream", "amp_stream_bf16", "amp_ct",
-        "umma_mb", "umma_wide_mb2", "umma_max_ctas", "umma_ntile_cap", "umma_tap_group", "umma_a_stages", "umma_stack", "umma_pair", "umma_pair_smem_kb", "_r0", "_r1", "_r2")]
+        "umma_mb", "umma_wide_mb2", "umma_max_ctas", "umma_ntile_cap", "umma_tap_group", "umma_a_stages", "umma_stack", "umma_pair", "umma_pair_smem_kb", "umma_pair_min", "_r1", "_r2")]
 
 
 class Tensor(C.Structure):

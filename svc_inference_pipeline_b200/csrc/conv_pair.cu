@@ -451,7 +451,8 @@ bool conv_pair_eligible(const bvg_conv_desc* d) {
   const bvg_conv_weights* w = d->w;
   if (tune_of(d->tune).umma_pair == 0) return false;
   if (!w || w->backend != BVG_UMMA || d->pre_amp || w->split == 2) return false;
-  if (w->n_tile < 128 || w->n_tile % 32 != 0 || w->n_total % 4 != 0) return false;
+  const int pair_min = tune_of(d->tune).umma_pair_min > 0 ? tune_of(d->tune).umma_pair_min : 128;
+  if (w->n_tile < pair_min || w->n_tile % 32 != 0 || w->n_total % 4 != 0) return false;
   if (w->split == 2) return false;
   if (w->split && w->n_tiles == 1 && tune_of(d->tune).umma_pair == 2) return false;  // A/B: C = 192 SPLIT layers on the single-CTA kernel
   const bool res = d->res.d_ptr != nullptr, acc = d->acc_in.d_ptr != nullptr;

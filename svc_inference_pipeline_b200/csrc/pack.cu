@@ -186,7 +186,8 @@ int conv_geometry(const bvg_conv_geom* g, bvg_conv_weights* w) {
   // per tap ("stacked", split = 2).  A_hi x [W_hi; W_lo] is then a single MMA of width 2 n_tile, so a product
   // costs two reads of the A tile from shared memory instead of three (these layers are bound by exactly that).
   // (a 128-column tile that the CTA-pair kernel takes keeps two separate planes: each CTA of the pair loads half of a box)
-  const bool for_pair = umma_pair && n_tile >= 128 && n_tile % 32 == 0 && n_total % 4 == 0;
+  const int pair_min = tune_of(g->tune).umma_pair_min > 0 ? tune_of(g->tune).umma_pair_min : 128;
+  const bool for_pair = umma_pair && n_tile >= pair_min && n_tile % 32 == 0 && n_total % 4 == 0;
   if (w->split && n_tile <= umma_stack && n_tile <= 128 && !for_pair) w->split = 2;
   const int n_tables = (g->backend == BVG_SIMT) ? 1 : w->n_tiles;
   BVG_REQUIRE(n_tables <= BVG_MAX_NTILES, "conv geometry: %d N tiles exceed BVG_MAX_NTILES", w->n_tiles);

@@ -12,6 +12,15 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # A/B aid: BVG_TEST_TUNE="knob=value,knob=value" runs the suite with those bvg_tuning knobs set in the binding
+    # (parity tests must hold under every supported setting; tests that pin the default geometry may not)
+    tune = os.environ.get("BVG_TEST_TUNE", "")
+    if tune:
+        from svc_inference_pipeline_b200 import _lib as L
+
+        for kv in tune.split(","):
+            k, v = kv.split("=")
+            L.set_tuning(k.strip(), int(v))
 
 
 @pytest.fixture(scope="session")
