@@ -515,3 +515,41 @@ def test_two_devices_in_one_process(golden):
         outs.append(m(torch.from_numpy(g["b1_snakebeta_log_mel"]).to(dev)).cpu())
     assert torch.equal(outs[0], outs[1])
     assert np.abs(outs[1].numpy() - g["b1_snakebeta_log_y_f64"]).max() < 1e-4
+
+
+def test_infer_chain_sampler_denormalise_vocoder(golden, repo_model):
+    """infer.py:79-86 on the device stages this package owns: svc_model_inference -> denormalize_mel_channel ->
+    synthesis_audios.  The sampler returns a transposed (non-contiguous) ``[n_mel, T]`` view on the device, which is what
+    the reference hands on; the result must equal the chain fed with a contiguous host copy of the same mel, and
+    the oracle's waveform for that mel (fp32 gate)."""
+    from svc_inference_pipeline_b200.modules.bigvgan_inference import synthesis_audios
+    from svc_inference_pipeline_b200.modules.diffsvc import DiffSVC
+    from svc_inference_pipeline_b200.modules.diffsvcrepo_inference import svc_model_inference
+    from svc_inference_pipeline_b200.utils import synth
+    from svc_inference_pipeline_b200.utils.acoustic_feature_extraction import denormalize_mel_channel
+    from svc_inference_pipeline_b200.utils.util import JsonHParams
+
+    g = golden("sampler.npz")
+    mapper = dict(noise_schedule_factors=[0.0001, 0.02, 1000], n_mel=100, residual_channels=64, diffusion_fc_size=128, conditioner_size=64,
+                  dilation_cycle_length=4, residual_kernel_size=3, residual_layer_num=4)
+    dm = DiffSVC(JsonHParams(**mapper))
+    dm.load_state_dict({k: torch.from_numpy(v) for k, v in synth.synthetic_diffsvc_state_dict(mapper, seed=5).items()})
+    dm = dm.to(DEV).eval()
+    cfg = JsonHParams(hop_length=256, fs=24000, mapper=JsonHParams(noise_schedule=g["noise_schedule"].tolist()))
+    batch = {"y": torch.zeros(*g["n1_x0"].shape, device=DEV), "cond": torch.from_numpy(g["n1_cond"]).to(DEV)}
+    nz = {"x0": torch.from_numpy(g["n1_x0"]), "steps": torch.from_numpy(g["n1_noise"]).to(DEV)}
+    y_pred = svc_model_inference([lambda b: b["cond"], dm], batch, cfg, noise=nz)            # [n_mel, T] in [-1, 1]
+    assert y_pred.is_cuda and tuple(y_pred.shape) == (100, 96) and not y_pred.is_contiguous()
+    assert np.abs(y_pred.cpu().numpy() - g["n1_y"]).max() < 2e-4
+    mel = denormalize_mel_channel(y_pred, cfg)                                                 # shipped default range (warns)
+    assert mel.is_cuda and float(mel.min()) >= -11.6 and float(mel.max()) <= 1.0
+    audio = synthesis_audios(repo_model, mel, cfg)
+    audio_host = synthesis_audios(repo_model, mel.cpu().contiguous(), cfg)
+    assert audio.shape == (96 * 256,) and np.array_equal(audio, audio_host)
+    from oracle import bigvgan_torch_cpu as P
+
+    tsd = {k: torch.from_numpy(v).double() for k, v in synth.synthetic_state_dict(REPO, seed=0).items()}
+    wave = P.generator_forward(tsd, REPO, mel.cpu().double().unsqueeze(0))[0, 0].numpy()     # the reference's op sequence, fp64
+    ref = O.synthesis_tail(wave, 96, 256)
+    assert np.abs(audio - ref).max() < 1e-4
+    assert np.isfinite(audio).all() and audio[-1] == 0.0
