@@ -174,8 +174,10 @@ int conv_geometry(const bvg_conv_geom* g, bvg_conv_weights* w) {
         const int t = ceil_div(base, cap);
         n_tile = round_up(ceil_div(base, t), 16);
         if (tr && g->cout % 16 == 0 && g->cout % n_tile != 0) n_tile = round_up(ceil_div(n_total, ceil_div(n_total, cap)), 16);
-        if (ceil_div(n_total, n_tile) <= BVG_MAX_NTILES || cap == cap_max) break;
-        cap = cap_max;  // a very wide transposed conv (8 x 768 output columns): keep the tile count inside the tap tables
+        if (ceil_div(n_total, n_tile) <= BVG_MAX_NTILES || cap >= 256) break;
+        // a very wide layer (a transposed conv with 8 x 768 output columns; 2C = 2048 at a 32-column cap): the cap is
+        // a preference, the per-tile tap tables (BVG_MAX_NTILES) are a limit -- widen until the tile count fits
+        cap = cap < cap_max ? cap_max : (cap * 2 > 256 ? 256 : cap * 2);
       }
     }
     BVG_REQUIRE(n_tile % 16 == 0 && n_tile >= 16 && n_tile <= 256, "conv geometry: UMMA n_tile %d must be a multiple of 16 in [16, 256]", n_tile);

@@ -370,3 +370,22 @@ def test_descriptor_validation_without_a_gpu():
     r.out = L.Tensor(p, None, L.F32, 0)
     assert lib.bvg_rowop_fwd(C.byref(r), None) == -1 and b"row pitch" in lib.bvg_last_error()
     assert lib.bvg_program_set_pdl(None, 1) == -1
+
+
+def test_tile_cap_is_a_preference_bounded_by_the_tap_tables():
+    """bvg_tuning.umma_ntile_cap narrows the N tiles (DiffSVC packs 32-column tiles for one utterance), but a layer too
+    wide for BVG_MAX_NTILES tiles of that width gets wider tiles instead of an error."""
+    from svc_inference_pipeline_b200 import _lib as L
+
+    def geom(cap, cin, cout, k, transposed=0, stride=1, pad=0):
+        t = L.new_tuning(umma_ntile_cap=cap)
+        g = L.ConvGeom(transposed, cin, cout, k, 1, stride, pad, L.UMMA, 1, 0, 1)
+        g.tune = C.pointer(t)
+        w = L.ConvWeights()
+        L.check(L.lib().bvg_conv_geometry(C.byref(g), C.byref(w)), "geometry")
+        return w.n_tile, w.n_tiles
+
+    assert geom(32, 384, 768, 3, pad=1) == (32, 24)
+    assert geom(32, 1024, 2048, 3, pad=1) == (64, 32)              # 64 tiles of 32 columns would not fit the tables
+    assert geom(64, 1536, 768, 8, 1, 4, 2) == (128, 24)            # transposed: 4 phases x 768 columns
+    assert geom(32, 1536, 768, 16, 1, 8, 4) == (256, 24)           # the v2 generator's first up-conv: 8 x 768 columns
