@@ -145,3 +145,29 @@ def test_denoiser_loader_reads_the_mapper_checkpoint(tmp_path):
     for k, v in sd.items():
         if k != "skip_projection.bias":
             np.testing.assert_array_equal(got[k].numpy(), v)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [dict(n_mel=80, residual_channels=512, conditioner_size=256, residual_layer_num=3, dilation_cycle_length=2, diffusion_fc_size=64),
+                                   dict(n_mel=128, residual_channels=1032, conditioner_size=72, residual_layer_num=2, dilation_cycle_length=1, diffusion_fc_size=256,
+                                        residual_kernel_size=5)])
+@pytest.mark.parametrize("B,Ln", [(1, 77), (3, 1500)])
+def test_denoiser_other_hyperparameters(shape, B, Ln):
+    """Mapper configurations other than the reference's (channel counts that are not multiples of 64, 2C beyond the tile
+    tables at the narrow cap, a 5-tap undilated kernel, row counts in every tile-width regime) against the fp64 oracle."""
+    from svc_inference_pipeline_b200.modules.diffsvc import DiffSVC
+
+    cfg = dict(MAPPER, **shape)
+    sdn = synth.synthetic_diffsvc_state_dict(cfg, seed=11)
+    sd = {k: torch.from_numpy(v) for k, v in sdn.items()}
+    m = DiffSVC(JsonHParams(**cfg), precision="fp32")
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    g = torch.Generator().manual_seed(B * 1000 + Ln)
+    mel, cond = torch.randn(B, Ln, cfg["n_mel"], generator=g), torch.randn(B, Ln, cfg["conditioner_size"], generator=g)
+    t = torch.randint(0, 1000, (B, 1), generator=g)
+    y, _ = m(mel.to(DEV), cond.to(DEV), t.to(DEV))
+    ref = DO.denoiser_forward(sd, cfg, mel.double(), cond.double(), t).numpy()
+    err = float(np.abs(y.cpu().numpy() - ref).max())
+    print(f"diffsvc {shape['residual_channels']}ch B{B}x{Ln}: max-abs vs fp64 oracle {err:.3e} (|y|max {np.abs(ref).max():.2f})")
+    assert err < 1e-4 * max(1.0, float(np.abs(ref).max()))
