@@ -327,6 +327,20 @@ __global__ void __launch_bounds__(PR_THREADS, 1) conv_pair_kernel(const __grid_c
           if (pb2 + u >= n_my) continue;
           const int c0 = it_c0[u];
           if (tbase >= p.L) continue;  // whole 32-row slab past the end of the sequence (warp-uniform)
+          const int n0 = nt * p.n_tile + c0 + 4 * g;
+          const long long off0 = (row_base + tbase + rrow) * N + n0;  // row i adds 8 * i * N
+          // running sum (acc_in): loaded before the accumulator leaves TMEM, so its latency runs under the TMEM read and
+          // the transposition through shared memory (ncu, DiffSVC dilated layer: tensor pipe 14 % active, the epilogue
+          // warps waiting on exactly these loads)
+          float ac[4][4];
+          if (ACC) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) ac[i][j] = 0.f;
+              if (n0 < N && tbase + rrow + 8 * i < p.L) epi_load4(p.epi.acc, SBF ? BVG_BF16 : BVG_F32, off0 + (long long)(8 * i) * N, ac[i]);
+            }
+          }
           uint32_t r[16];
           ptx::tmem_ld16(tmem_q + (uint32_t)c0, r);
           if (corr_separate) {
@@ -344,7 +358,6 @@ __global__ void __launch_bounds__(PR_THREADS, 1) conv_pair_kernel(const __grid_c
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r[4 * gg]), "r"(r[4 * gg + 1]), "r"(r[4 * gg + 2]), "r"(r[4 * gg + 3]) : "memory");
           }
           __syncwarp();
-          const int n0 = nt * p.n_tile + c0 + 4 * g;
           float v[4][4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -357,16 +370,9 @@ __global__ void __launch_bounds__(PR_THREADS, 1) conv_pair_kernel(const __grid_c
           __syncwarp();
           if (n0 >= N) continue;
           const float4 bias = *reinterpret_cast<const float4*>(p.epi.bias + n0);
-          const long long off0 = (row_base + tbase + rrow) * N + n0;  // row i adds 8 * i * N
-          float ac[4][4];
-          if (ACC) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) ac[i][j] = 0.f;
-              if (tbase + rrow + 8 * i < p.L) epi_load4(p.epi.acc, SBF ? BVG_BF16 : BVG_F32, off0 + (long long)(8 * i) * N, ac[i]);
-            }
-          }
+          // per-channel divisor: one load per chunk, next to the bias (inside the row loop it was a dependent global load
+          // in front of every division: ncu's top long-scoreboard stall of the DiffSVC output projection)
+          const float4 cd = p.epi.coldiv ? __ldg(reinterpret_cast<const float4*>(p.epi.coldiv + n0)) : make_float4(1.f, 1.f, 1.f, 1.f);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             if (tbase + rrow + 8 * i >= p.L) continue;
@@ -392,7 +398,6 @@ __global__ void __launch_bounds__(PR_THREADS, 1) conv_pair_kernel(const __grid_c
               for (int j = 0; j < 4; ++j) v[i][j] = __fdiv_rn(v[i][j], p.epi.div);
             }
             if (p.epi.coldiv) {
-              const float4 cd = *reinterpret_cast<const float4*>(p.epi.coldiv + n0);
               v[i][0] = __fdiv_rn(v[i][0], cd.x); v[i][1] = __fdiv_rn(v[i][1], cd.y);
               v[i][2] = __fdiv_rn(v[i][2], cd.z); v[i][3] = __fdiv_rn(v[i][3], cd.w);
             }

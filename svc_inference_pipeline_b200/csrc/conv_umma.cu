@@ -551,6 +551,8 @@ __global__ void __launch_bounds__(FUSED ? UM_THREADS_FUSED : 128 + 32 * UM_EPI_W
           if (n0 >= N) continue;
           if (!GEN || p.vec_ok) {
             const float4 bias = *reinterpret_cast<const float4*>(p.epi.bias + n0);
+            [[maybe_unused]] float4 cd = make_float4(1.f, 1.f, 1.f, 1.f);  // per-channel divisor: one load per chunk
+            if (GEN && p.epi.coldiv) cd = __ldg(reinterpret_cast<const float4*>(p.epi.coldiv + n0));
             const long long off0 = (row_base + tbase + rrow) * N + n0;  // row i adds 8 * i * N
             float ac[4][4];
             if (has_acc) {
@@ -589,7 +591,6 @@ __global__ void __launch_bounds__(FUSED ? UM_THREADS_FUSED : 128 + 32 * UM_EPI_W
                 for (int j = 0; j < 4; ++j) v[i][j] = __fdiv_rn(v[i][j], p.epi.div);
               }
               if (GEN && p.epi.coldiv) {
-                const float4 cd = *reinterpret_cast<const float4*>(p.epi.coldiv + n0);
                 v[i][0] = __fdiv_rn(v[i][0], cd.x); v[i][1] = __fdiv_rn(v[i][1], cd.y);
                 v[i][2] = __fdiv_rn(v[i][2], cd.z); v[i][3] = __fdiv_rn(v[i][3], cd.w);
               }
