@@ -294,10 +294,25 @@ __global__ void __launch_bounds__(PR_THREADS, 1) conv_pair_kernel(const __grid_c
       const int tbase = t0 + q * 32;
       for (int pb2 = 0; pb2 < n_my; pb2 += 2) {
         uint4 raw[2][4];
+        [[maybe_unused]] float ac[2][4][4];
         int it_c0[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           it_c0[u] = (grp + 2 * (pb2 + u)) << 4;
+          if (ACC) {
+            // running sum (acc_in) of both chunks of this iteration, issued together and -- for the first pair of a tile --
+            // before the accumulator-ready wait, like the residuals below (ncu on the DiffSVC dilated layer: tensor pipe
+            // 14 % active, the epilogue warps stalled on exactly these loads when they were issued chunk by chunk)
+            const int n0 = nt * p.n_tile + it_c0[u] + 4 * g;
+            const bool ok = pb2 + u < n_my && n0 < N;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) ac[u][i][j] = 0.f;
+              const int t = tbase + rrow + 8 * i;
+              if (ok && t < p.L) epi_load4(p.epi.acc, SBF ? BVG_BF16 : BVG_F32, (row_base + t) * N + n0, ac[u][i]);
+            }
+          }
           if (RES) {
             const int n0 = nt * p.n_tile + it_c0[u] + 4 * g;
             const bool ok = pb2 + u < n_my && n0 < N;
@@ -329,18 +344,6 @@ __global__ void __launch_bounds__(PR_THREADS, 1) conv_pair_kernel(const __grid_c
           if (tbase >= p.L) continue;  // whole 32-row slab past the end of the sequence (warp-uniform)
           const int n0 = nt * p.n_tile + c0 + 4 * g;
           const long long off0 = (row_base + tbase + rrow) * N + n0;  // row i adds 8 * i * N
-          // running sum (acc_in): loaded before the accumulator leaves TMEM, so its latency runs under the TMEM read and
-          // the transposition through shared memory (ncu, DiffSVC dilated layer: tensor pipe 14 % active, the epilogue
-          // warps waiting on exactly these loads)
-          float ac[4][4];
-          if (ACC) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) ac[i][j] = 0.f;
-              if (n0 < N && tbase + rrow + 8 * i < p.L) epi_load4(p.epi.acc, SBF ? BVG_BF16 : BVG_F32, off0 + (long long)(8 * i) * N, ac[i]);
-            }
-          }
           uint32_t r[16];
           ptx::tmem_ld16(tmem_q + (uint32_t)c0, r);
           if (corr_separate) {
@@ -391,7 +394,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) conv_pair_kernel(const __grid_c
             }
             if (ACC) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) v[i][j] += ac[i][j];
+              for (int j = 0; j < 4; ++j) v[i][j] += ac[u][i][j];
             }
             if (p.epi.use_div) {
 #pragma unroll
