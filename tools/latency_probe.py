@@ -1,3 +1,6 @@
+"""Where the wall-clock time of one utterance through synthesis_audios goes (configs[0]: 379 frames): H2D, forward as
+launch list / CUDA graph / with programmatic dependent launch, D2H, host tail.
+    python tools/latency_probe.py"""
 import os, sys, time
 sys.path.insert(0, "/root/repo")
 import torch, numpy as np
